@@ -1,0 +1,218 @@
+/* b2r.h -- C ABI of the B200-native render hot paths (libb2r.so).
+ *
+ * Drop-in boundary for the two `void Draw()` functions of
+ * ArchDD/CPP-Raytracer-Rasterizer:
+ *     raytracer/Source/raytracer.cpp:547-606    (Draw -> ClosestIntersection -> DirectLight)
+ *     rasteriser/Source/rasteriser.cpp:461-482  (Draw -> DrawPolygon -> ... -> PixelShader)
+ * The reference has no FFI: Draw() takes no arguments and talks through
+ * file-scope globals.  This header is what a binding of that path looks like
+ * once the globals are made explicit: plain pointers and sizes, POD structs
+ * whose fields are the reference's globals (cited per field), no C++ or torch
+ * types.  Every function returns 0 on success or a negative B2R_E_* code and
+ * never throws or exits; b2r_last_error() gives the text.
+ *
+ * Ownership: the context owns all device memory; the caller owns every host
+ * pointer it passes; no host pointer is retained after a call returns.
+ * Threading: one context per GPU and per host thread (externally
+ * synchronised).  All calls are synchronous on return unless named *_async.
+ */
+#ifndef B2R_H
+#define B2R_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_ABI_VERSION 1
+
+#define B2R_MAX_LIGHTS 32         /* Light lights[32]: raytracer.cpp:48, rasteriser.cpp:50 */
+#define B2R_RANDOM_POSITIONS 256  /* vec3 randomPositions[256]: raytracer.cpp:84 */
+
+enum {
+    B2R_OK = 0,
+    B2R_E_INVALID = -1,    /* bad argument */
+    B2R_E_CUDA = -2,       /* CUDA runtime error (text in b2r_last_error) */
+    B2R_E_NO_SCENE = -3,   /* draw before b2r_set_triangles / b2r_set_frame */
+    B2R_E_UNSUPPORTED = -4,
+    B2R_E_IO = -5,
+    B2R_E_CAPACITY = -6    /* a projected triangle exceeds the row limit (see b2r_ras_draw) */
+};
+
+/* == reference `class Light` (raytracer TestModel.h:35-45), 28 bytes */
+typedef struct b2r_light {
+    float position[3];
+    float color[3];
+    float intensity;
+} b2r_light;
+
+/* == reference `struct Intersection` (raytracer.cpp:91-96), 20 bytes */
+typedef struct b2r_intersection {
+    float position[3];
+    float distance;
+    int32_t triangleIndex;
+} b2r_intersection;
+
+/* The globals Draw() reads, made explicit. */
+typedef struct b2r_frame_params {
+    float cameraPos[3];        /* raytracer.cpp:70, rasteriser.cpp:39 */
+    float cameraRot[9];        /* glm::mat3 memory order (column-major): raytracer.cpp:73, rasteriser.cpp:40 */
+    float focalLength;         /* raytracer.cpp:69, rasteriser.cpp:41 */
+    int32_t numLights;         /* NUM_LIGHTS: raytracer.cpp:47, rasteriser.cpp:49 */
+    b2r_light lights[B2R_MAX_LIGHTS];
+    float randomPositions[B2R_RANDOM_POSITIONS * 3]; /* raytracer.cpp:84 (soft-shadow jitter table; an INPUT) */
+    int32_t aaEnabled;         /* AA_ENABLED raytracer.cpp:37 */
+    int32_t aaSamples;         /* AA_SAMPLES raytracer.cpp:38 */
+    int32_t softShadowsEnabled;/* SOFT_SHADOWS_ENABLED raytracer.cpp:40 */
+    int32_t softShadowsSamples;/* SOFT_SHADOWS_SAMPLES raytracer.cpp:41 */
+    float indirectLight[3];    /* raytracer.cpp:81 / indirectLightPowerPerArea rasteriser.cpp:47 */
+    float dofFocalLength;      /* FOCAL_LENGTH raytracer.cpp:45 / rasteriser.cpp:31 */
+    float currentReflectance[3]; /* rasteriser.cpp:46,466 */
+    int32_t dofEnabled;        /* DOF_ENABLED raytracer.cpp:43 / rasteriser.cpp:29 */
+    int32_t dofKernelSize;     /* DOF_KERNEL_SIZE raytracer.cpp:44 / rasteriser.cpp:30 */
+    int32_t backfaceCulling;   /* BACKFACE_CULLING_ENABLED rasteriser.cpp:26 */
+    int32_t frustumCulling;    /* FRUSTUM_CULLING_ENABLED rasteriser.cpp:27 */
+} b2r_frame_params;
+
+typedef struct b2r_ctx b2r_ctx;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int b2r_abi_version(void);
+/* One context per GPU; width/height are SCREEN_WIDTH/SCREEN_HEIGHT (raytracer.cpp:67-68). */
+int b2r_create(b2r_ctx** out, int device, int width, int height);
+int b2r_destroy(b2r_ctx* ctx);
+/* Last error text of this context (or of b2r_create when ctx == NULL). */
+const char* b2r_last_error(const b2r_ctx* ctx);
+/* Fills frame params with the reference's start-up defaults for the raytracer
+ * (which = 0: raytracer.cpp:33-81,116,162) or the rasteriser (which = 1:
+ * rasteriser.cpp:22-50,104,115), scaled to the given screen size the way the
+ * reference scales them (focalLength = H/2 resp. H). */
+int b2r_default_frame_params(b2r_frame_params* out, int which, int width, int height);
+
+/* ---- scene -------------------------------------------------------------- */
+/* The global `vector<Triangle> triangles` (raytracer.cpp:28, rasteriser.cpp:64)
+ * as the reference lays it out in memory: stride 60 (raytracer Triangle:
+ * v0,v1,v2,normal,color) or 64 (rasteriser Triangle: + bool isCulled at byte
+ * 60).  Copied to the device; the host pointer is not retained. */
+int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride_bytes);
+/* Replaces only the isCulled flags (rasteriser.cpp:404-447 writes them each frame). */
+int b2r_set_culled(b2r_ctx* ctx, const uint8_t* culled, int count);
+int b2r_set_frame(b2r_ctx* ctx, const b2r_frame_params* params);
+
+/* ---- raytracer: Draw() of raytracer.cpp:547-606 ------------------------- */
+/* Renders rows [y0,y1) (0,H for the whole frame; a band for multi-GPU splits).
+ * Includes the per-frame precondition of Update() (raytracer.cpp:335-339):
+ * every pixel's Intersection starts at distance FLT_MAX.  Outputs (each may be
+ * NULL) are FULL-FRAME host arrays indexed y*width+x; only rows [y0,y1) are
+ * written:
+ *   pixelColours          3 floats/pixel  (raytracer.cpp:88,600)
+ *   closestIntersections  20 bytes/pixel  (raytracer.cpp:98); pixels never hit
+ *                         get distance FLT_MAX, triangleIndex -1, position 0
+ *   focalDistances        1 float/pixel   (raytracer.cpp:87,249); 0 where never hit */
+int b2r_rt_draw(b2r_ctx* ctx, int y0, int y1, float* pixelColours,
+                b2r_intersection* closestIntersections, float* focalDistances);
+
+/* ---- rasteriser: Draw() of rasteriser.cpp:461-482 ----------------------- */
+/* Includes the per-frame clears of Update() (rasteriser.cpp:183-192).  Outputs
+ * (each may be NULL), full-frame host arrays, rows [y0,y1) written:
+ *   depthBuffer     1 float/pixel (rasteriser.cpp:52), 0 where nothing drawn
+ *   pixelColours    3 floats/pixel (rasteriser.cpp:69,588)
+ *   focalDistances  1 float/pixel (rasteriser.cpp:68,565), 0 where nothing drawn
+ *   winnerIndex     index of the triangle that owns the depth-buffer value
+ *                   (the reference keeps none; oracle patch P4), -1 if none */
+int b2r_ras_draw(b2r_ctx* ctx, int y0, int y1, float* depthBuffer, float* pixelColours,
+                 float* focalDistances, int32_t* winnerIndex);
+/* The culling block of Update() (rasteriser.cpp:385-447) on the device: writes
+ * Triangle::isCulled for the current frame params.  culledOut may be NULL. */
+int b2r_ras_cull(b2r_ctx* ctx, uint8_t* culledOut);
+
+/* ---- resolve: CalculateDOF() + PutPixelSDL ------------------------------ */
+/* raytracer.cpp:608-656 == rasteriser.cpp:484-529, SDLauxiliary.h:70-81.
+ * Converts the pixelColours of the last draw on this context to the 32-bit
+ * XRGB surface the reference fills (interior pixels only; the 1-pixel border
+ * stays 0).  Applies the depth-of-field blur when params.dofEnabled.
+ * surface: width*height uint32 (0x00RRGGBB), host memory. */
+int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface);
+/* Same pixels as 24-bit bottom-up BGR rows padded to 4 bytes (the payload
+ * SDL_SaveBMP writes, raytracer.cpp:175).  bgr: b2r_bmp_payload_bytes(). */
+int b2r_resolve_bgr8(b2r_ctx* ctx, uint8_t* bgr);
+size_t b2r_bmp_payload_bytes(int width, int height);
+/* Headless replacement of SDL_SaveBMP(screen, path). */
+int b2r_write_bmp(const char* path, const uint8_t* bgr_payload, int width, int height);
+
+/* One call per frame, the Draw() drop-ins: draw + resolve, copy out only what is asked for.
+ * surface may be NULL.  Extra outputs as in b2r_rt_draw / b2r_ras_draw, may be NULL. */
+int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* pixelColours,
+                 b2r_intersection* closestIntersections, float* focalDistances);
+int b2r_ras_frame(b2r_ctx* ctx, uint32_t* surface, float* depthBuffer, float* pixelColours,
+                  float* focalDistances, int32_t* winnerIndex);
+
+/* ---- device-resident entry points (no host copies) ---------------------- */
+/* For callers that keep frames in HBM (multi-GPU band gathers, benchmarks).
+ * All pointers are DEVICE pointers on the context's GPU, full-frame arrays as
+ * above, may be NULL.  Work is enqueued on the context's stream;
+ * b2r_synchronize() waits for it.  cuda_stream (a cudaStream_t cast to void*)
+ * replaces the context's own stream when non-NULL at b2r_set_stream(). */
+int b2r_set_stream(b2r_ctx* ctx, void* cuda_stream);
+void* b2r_get_stream(b2r_ctx* ctx);
+int b2r_synchronize(b2r_ctx* ctx);
+int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_pixelColours,
+                             b2r_intersection* d_closestIntersections, float* d_focalDistances);
+int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_depthBuffer,
+                              float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
+/* Resolve rows [y0,y1) of d_pixelColours (+ d_focalDistances when DOF is on) into d_surface. */
+int b2r_resolve_surface_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_pixelColours,
+                                     const float* d_focalDistances, uint32_t* d_surface);
+
+/* ---- introspection ------------------------------------------------------ */
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+unsigned long long b2r_launch_count(const b2r_ctx* ctx);
+/* Counters of the last draw: see B2R_STAT_* indices; out must hold B2R_STAT_COUNT values. */
+enum {
+    B2R_STAT_PRIMARY_RAYS = 0,  /* ClosestIntersection calls from Draw (raytracer.cpp:580) */
+    B2R_STAT_SHADOW_RAYS = 1,   /* ClosestIntersection calls from DirectLight (raytracer.cpp:310) */
+    B2R_STAT_EXACT_TESTS = 2,   /* ray/triangle pairs that reached the exact (reference-order) evaluation */
+    B2R_STAT_RAS_TRIANGLES = 3, /* triangles drawn (not culled) */
+    B2R_STAT_RAS_ROWS = 4,      /* polygon rows produced by ComputePolygonRows */
+    B2R_STAT_RAS_DEPTH_TESTS = 5, /* on-screen depth tests (rasteriser.cpp:606) */
+    B2R_STAT_COUNT = 8
+};
+int b2r_get_stats(b2r_ctx* ctx, unsigned long long* out);
+/* Counters cost atomics, so they are off by default; when on, every draw also fills them. */
+int b2r_enable_stats(b2r_ctx* ctx, int on);
+/* Tuning/diagnostic switches (B2R_OPT_*); results are identical for every setting. */
+enum {
+    B2R_OPT_RT_FILTER = 0,   /* 1 (default): conservative FMA filter ahead of the exact reference-order test; 0: exact test on every ray/triangle pair */
+    B2R_OPT_RT_VARIANT = 1,  /* raytracer kernel variant, see DESIGN.md */
+    B2R_OPT_RAS_VARIANT = 2  /* rasteriser pipeline variant, see DESIGN.md */
+};
+int b2r_set_option(b2r_ctx* ctx, int option, int value);
+/* Device FP32 FFMA throughput microbenchmark (TFLOP/s), the raytracer's roofline denominator. */
+int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds);
+
+/* ---- host-side scene helpers (no GPU involved) ---------------------------- */
+/* LoadTestModel (raytracer TestModel.h:51-192 == rasteriser TestModel.h:151-292): the 30-triangle
+ * Cornell box, written as reference Triangle records of the given stride (60 or 64).  Returns the
+ * triangle count or a negative error. */
+int b2r_scene_cornell_box(void* out, int capacity, int stride_bytes);
+/* Uniform k*k tessellation of every input triangle, parent order kept:
+ * P(i,j) = A + (i/k)(B-A) + (j/k)(C-A); per j then i: "up" (P(i,j),P(i+1,j),P(i,j+1)) and, if
+ * i+j < k-1, "down" (P(i+1,j),P(i+1,j+1),P(i,j+1)); normals recomputed like the Triangle ctor
+ * (TestModel.h:26-31).  out may be NULL to query the count.  Returns the output count. */
+long long b2r_scene_tessellate(const void* in, int count, int in_stride, int k, void* out, int out_stride);
+/* cameraRot as Update() builds it from yaw (raytracer.cpp:377-382, rasteriser.cpp:378-383);
+ * rot11 is the preset [1][1] element: 1.0f (raytracer.cpp:162) or 1.01f (rasteriser.cpp:115). */
+int b2r_camera_rot_from_yaw(float yaw, float rot11, float* rot9_colmajor);
+/* Orbit animation camera: yaw = frame*2pi/nframes,
+ * cameraPos = -radius*forward, rotation as above with rot11 = 1. */
+int b2r_orbit_camera(int frame, int nframes, float radius, float* cameraPos3, float* rot9_colmajor);
+/* The soft-shadow jitter table AddLight() derives from glibc rand() after srand(seed)
+ * (raytracer.cpp:186-190,260-263) for light 0 at lightPos; entries 16..255 are 0. */
+int b2r_jitter_table(unsigned seed, const float* lightPos3, float* out768);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H */
