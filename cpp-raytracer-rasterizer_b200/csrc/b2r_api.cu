@@ -1,0 +1,554 @@
+// b2r_api.cu -- the extern "C" layer declared in include/b2r.h.
+//
+// Owns the context (device buffers, stream, per-frame constants) and maps the
+// reference's implicit Draw() contract (globals in, globals out) onto explicit
+// calls.  No CPU rendering path exists here: every draw is a CUDA launch.
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "b2r_internal.h"
+#include "exact.cuh"
+
+using namespace b2r;
+
+namespace {
+
+thread_local std::string g_createError;
+
+int fail(Ctx* c, int code, const char* what) {
+    if (c) c->err = what;
+    return code;
+}
+
+int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    if (c) c->err = buf;
+    else g_createError = buf;
+    cudaGetLastError();  // clear the sticky-less error state
+    return B2R_E_CUDA;
+}
+
+#define CU(call, what)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(c, e__, what); \
+    } while (0)
+
+int bind(Ctx* c) {
+    if (!c) return B2R_E_INVALID;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaSetDevice");
+    return B2R_OK;
+}
+
+// glm::inverse(mat3) in GLM's operation order (glm/detail/type_mat3x3.inl:36-57); m, out column-major.
+void inverse3(const float* m, float* o) {
+#define M(c, r) m[3 * (c) + (r)]
+    const float ood = xdiv(1.0f, xadd(xsub(xmul(+M(0, 0), xsub(xmul(M(1, 1), M(2, 2)), xmul(M(2, 1), M(1, 2)))),
+                                           xmul(M(1, 0), xsub(xmul(M(0, 1), M(2, 2)), xmul(M(2, 1), M(0, 2))))),
+                                      xmul(M(2, 0), xsub(xmul(M(0, 1), M(1, 2)), xmul(M(1, 1), M(0, 2))))));
+    o[3 * 0 + 0] = xmul(+xsub(xmul(M(1, 1), M(2, 2)), xmul(M(2, 1), M(1, 2))), ood);
+    o[3 * 1 + 0] = xmul(-xsub(xmul(M(1, 0), M(2, 2)), xmul(M(2, 0), M(1, 2))), ood);
+    o[3 * 2 + 0] = xmul(+xsub(xmul(M(1, 0), M(2, 1)), xmul(M(2, 0), M(1, 1))), ood);
+    o[3 * 0 + 1] = xmul(-xsub(xmul(M(0, 1), M(2, 2)), xmul(M(2, 1), M(0, 2))), ood);
+    o[3 * 1 + 1] = xmul(+xsub(xmul(M(0, 0), M(2, 2)), xmul(M(2, 0), M(0, 2))), ood);
+    o[3 * 2 + 1] = xmul(-xsub(xmul(M(0, 0), M(2, 1)), xmul(M(2, 0), M(0, 1))), ood);
+    o[3 * 0 + 2] = xmul(+xsub(xmul(M(0, 1), M(1, 2)), xmul(M(1, 1), M(0, 2))), ood);
+    o[3 * 1 + 2] = xmul(-xsub(xmul(M(0, 0), M(1, 2)), xmul(M(1, 0), M(0, 2))), ood);
+    o[3 * 2 + 2] = xmul(+xsub(xmul(M(0, 0), M(1, 1)), xmul(M(1, 0), M(0, 1))), ood);
+#undef M
+}
+
+int ensure_pinned(Ctx* c, size_t bytes) {
+    if (bytes <= c->pinnedCap) return B2R_OK;
+    if (c->pinned) cudaFreeHost(c->pinned);
+    c->pinned = nullptr;
+    c->pinnedCap = 0;
+    CU(cudaMallocHost(&c->pinned, bytes), "cudaMallocHost");
+    c->pinnedCap = bytes;
+    return B2R_OK;
+}
+
+int reset_stats(Ctx* c) {
+    if (!c->statsOn) return B2R_OK;
+    CU(c->stats.reserve(sizeof(unsigned long long) * B2R_STAT_COUNT), "stats alloc");
+    CU(cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long) * B2R_STAT_COUNT, c->stream), "stats clear");
+    return B2R_OK;
+}
+
+int check_band(Ctx* c, int y0, int y1) {
+    if (y0 < 0 || y1 > c->H || y0 > y1) return fail(c, B2R_E_INVALID, "row band outside [0,H]");
+    if (!c->haveScene) return fail(c, B2R_E_NO_SCENE, "b2r_set_triangles has not been called");
+    if (!c->haveFrame) return fail(c, B2R_E_NO_SCENE, "b2r_set_frame has not been called");
+    return B2R_OK;
+}
+
+// D2H of rows [y0,y1) of a full-frame array with `bpp` bytes per pixel.
+int copy_rows_out(Ctx* c, void* host, const void* dev, int y0, int y1, size_t bpp) {
+    if (!host || y1 <= y0) return B2R_OK;
+    const size_t off = (size_t)y0 * c->W * bpp, bytes = (size_t)(y1 - y0) * c->W * bpp;
+    CU(cudaMemcpyAsync((char*)host + off, (const char*)dev + off, bytes, cudaMemcpyDeviceToHost, c->stream), "D2H copy");
+    return B2R_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2r_abi_version(void) { return B2R_ABI_VERSION; }
+
+const char* b2r_last_error(const b2r_ctx* ctx) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    return c ? c->err.c_str() : g_createError.c_str();
+}
+
+int b2r_create(b2r_ctx** out, int device, int width, int height) {
+    Ctx* c = nullptr;
+    if (!out || width <= 0 || height <= 0 || width > 32768 || height > 32768) {
+        g_createError = "b2r_create: bad arguments";
+        return B2R_E_INVALID;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return cuda_fail(nullptr, e == cudaSuccess ? cudaErrorNoDevice : e,
+                         "b2r_create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= count) {
+        g_createError = "b2r_create: device index out of range";
+        return B2R_E_INVALID;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cuda_fail(nullptr, e, "cudaSetDevice");
+    c = new (std::nothrow) Ctx();
+    if (!c) return B2R_E_CUDA;
+    c->device = device;
+    c->W = width;
+    c->H = height;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+    }
+    c->smCount = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return cuda_fail(nullptr, e, "cudaStreamCreate");
+    }
+    c->stream = c->ownStream;
+    if ((e = cudaMallocHost((void**)&c->pinnedFrame, sizeof(DevFrame))) != cudaSuccess ||
+        (e = cudaMallocHost(&c->pinned, 4096)) != cudaSuccess || (e = c->frame.reserve(sizeof(DevFrame))) != cudaSuccess) {
+        b2r_destroy(reinterpret_cast<b2r_ctx*>(c));
+        return cuda_fail(nullptr, e, "b2r_create: allocation");
+    }
+    c->pinnedCap = 4096;
+    *out = reinterpret_cast<b2r_ctx*>(c);
+    return B2R_OK;
+}
+
+int b2r_destroy(b2r_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return B2R_OK;
+    cudaSetDevice(c->device);
+    if (c->ownStream) cudaStreamSynchronize(c->ownStream);
+    DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->stats};
+    for (DevBuf* b : bufs) b->release();
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+    return B2R_OK;
+}
+
+int b2r_set_stream(b2r_ctx* ctx, void* cuda_stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return B2R_E_INVALID;
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->ownStream;
+    return B2R_OK;
+}
+
+void* b2r_get_stream(b2r_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    return c ? reinterpret_cast<void*>(c->stream) : nullptr;
+}
+
+int b2r_synchronize(b2r_ctx* ctx) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    CU(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
+    return B2R_OK;
+}
+
+int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (count < 0 || (count > 0 && !triangles) || (stride != 60 && stride != 64))
+        return fail(c, B2R_E_INVALID, "b2r_set_triangles: stride must be 60 (raytracer Triangle) or 64 (rasteriser Triangle)");
+    CU(cudaStreamSynchronize(c->stream), "sync before scene upload");
+    const size_t bytes = (size_t)count * stride;
+    CU(c->raw.reserve(bytes + 64), "scene alloc");
+    CU(c->culled.reserve((size_t)count + 64), "scene alloc");
+    CU(c->geom.reserve((size_t)count * kGeomQuads * 16 + 64), "scene alloc");
+    if (count) CU(cudaMemcpyAsync(c->raw.p, triangles, bytes, cudaMemcpyHostToDevice, c->stream), "scene upload");
+    c->T = count;
+    c->stride = stride;
+    // isCulled: byte 60 of the 64-byte rasteriser Triangle; the raytracer Triangle has none
+    if (count) {
+        if (int rc = ensure_pinned(c, (size_t)count + 64)) return rc;
+        unsigned char* m = (unsigned char*)c->pinned;
+        for (int i = 0; i < count; ++i) m[i] = (stride == 64) ? (((const unsigned char*)triangles)[(size_t)i * 64 + 60] != 0) : 0;
+        CU(cudaMemcpyAsync(c->culled.p, m, (size_t)count, cudaMemcpyHostToDevice, c->stream), "culled upload");
+    }
+    CU(launch_tri_prep(c, c->stream), "tri_prep_kernel");
+    CU(cudaStreamSynchronize(c->stream), "scene upload");
+    c->haveScene = true;
+    return B2R_OK;
+}
+
+int b2r_set_culled(b2r_ctx* ctx, const uint8_t* culled, int count) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!c->haveScene || count != c->T || (count > 0 && !culled)) return fail(c, B2R_E_INVALID, "b2r_set_culled: count must equal the triangle count");
+    if (count == 0) return B2R_OK;
+    CU(cudaStreamSynchronize(c->stream), "sync");
+    if (int rc = ensure_pinned(c, (size_t)count + 64)) return rc;
+    memcpy(c->pinned, culled, (size_t)count);
+    CU(cudaMemcpyAsync(c->culled.p, c->pinned, (size_t)count, cudaMemcpyHostToDevice, c->stream), "culled upload");
+    CU(cudaStreamSynchronize(c->stream), "culled upload");
+    return B2R_OK;
+}
+
+int b2r_set_frame(b2r_ctx* ctx, const b2r_frame_params* p) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!p) return fail(c, B2R_E_INVALID, "b2r_set_frame: null params");
+    if (p->numLights < 0 || p->numLights > B2R_MAX_LIGHTS) return fail(c, B2R_E_INVALID, "numLights outside [0,32]");
+    const int N = p->aaEnabled ? p->aaSamples : 1;                       // raytracer.cpp:551-554
+    const int samples = p->softShadowsEnabled ? p->softShadowsSamples : 1;  // raytracer.cpp:272-275
+    if (N < 1 || N > 64) return fail(c, B2R_E_INVALID, "aaSamples outside [1,64]");
+    if (samples < 1) return fail(c, B2R_E_INVALID, "softShadowsSamples < 1");
+    if (samples != 1 && p->numLights * samples > B2R_RANDOM_POSITIONS)
+        return fail(c, B2R_E_INVALID, "numLights*softShadowsSamples exceeds randomPositions[256] (raytracer.cpp:84)");
+    if (p->dofEnabled && (p->dofKernelSize < 1 || p->dofKernelSize > 64)) return fail(c, B2R_E_INVALID, "dofKernelSize outside [1,64]");
+
+    DevFrame& f = c->hostFrame;
+    memset(&f, 0, sizeof f);
+    for (int i = 0; i < 3; ++i) {
+        f.cam[i] = p->cameraPos[i];
+        f.indirect[i] = p->indirectLight[i];
+        f.reflectance[i] = p->currentReflectance[i];
+    }
+    for (int i = 0; i < 9; ++i) f.R[i] = p->cameraRot[i];
+    inverse3(p->cameraRot, f.Rinv);  // rasteriser.cpp:559 (per pixel in the reference; same bits every time)
+    f.focal = p->focalLength;
+    f.dofFocal = p->dofFocalLength;
+    f.nLights = p->numLights;
+    f.samples = samples;
+    f.aaN = N;
+    f.nOrigins = 1 + p->numLights * samples;
+    f.dofEnabled = p->dofEnabled;
+    f.dofKernel = p->dofKernelSize;
+    // bound on |cameraRot * (x1 - W/2, y1 - H/2, focalLength)|_inf over every sub-sample of the frame
+    {
+        const double ax = c->W / 2.0 + 2.0, ay = c->H / 2.0 + 2.0, az = fabs((double)p->focalLength);
+        double dmax = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            double v = fabs((double)p->cameraRot[r]) * ax + fabs((double)p->cameraRot[3 + r]) * ay +
+                       fabs((double)p->cameraRot[6 + r]) * az;
+            if (v > dmax) dmax = v;
+        }
+        f.primaryDmax = (float)(dmax * 1.0001);
+        if (!(f.primaryDmax > 0.f) || !isfinite(f.primaryDmax)) f.primaryDmax = FLT_MAX;  // filter never rejects
+    }
+    for (int i = 0; i < 3; ++i) f.origin[0][i] = p->cameraPos[i];
+    for (int k = 0; k < p->numLights; ++k) {
+        const b2r_light& L = p->lights[k];
+        for (int i = 0; i < 3; ++i) {
+            f.lightPos[k][i] = L.position[i];
+            f.lightColor[k][i] = xmul(L.color[i], L.intensity);                 // raytracer.cpp:282, rasteriser.cpp:577
+            f.lightPower[k][i] = xdiv(f.lightColor[k][i], (float)samples);      // raytracer.cpp:296
+        }
+        for (int s = 0; s < samples; ++s) {
+            // raytracer.cpp:284-291: the jitter table when soft shadows are on, else the light itself
+            const float* src = (samples != 1) ? &p->randomPositions[3 * (k * p->softShadowsSamples + s)] : L.position;
+            for (int i = 0; i < 3; ++i) f.origin[1 + k * samples + s][i] = src[i];
+        }
+    }
+    c->params = *p;
+    CU(cudaStreamSynchronize(c->stream), "sync before frame upload");  // pinnedFrame may still be in flight
+    memcpy(c->pinnedFrame, &f, sizeof f);
+    const size_t used = offsetof(DevFrame, origin) + sizeof(float) * 4 * (size_t)f.nOrigins;
+    CU(cudaMemcpyAsync(c->frame.p, c->pinnedFrame, used, cudaMemcpyHostToDevice, c->stream), "frame upload");
+    c->haveFrame = true;
+    return B2R_OK;
+}
+
+int b2r_set_option(b2r_ctx* ctx, int option, int value) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return B2R_E_INVALID;
+    switch (option) {
+        case B2R_OPT_RT_FILTER: c->optRtFilter = value ? 1 : 0; return B2R_OK;
+        case B2R_OPT_RT_VARIANT: c->optRtVariant = value; return B2R_OK;
+        case B2R_OPT_RAS_VARIANT: c->optRasVariant = value; return B2R_OK;
+    }
+    return fail(c, B2R_E_INVALID, "unknown option");
+}
+
+int b2r_enable_stats(b2r_ctx* ctx, int on) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    c->statsOn = on != 0;
+    if (c->statsOn) {
+        CU(c->stats.reserve(sizeof(unsigned long long) * B2R_STAT_COUNT), "stats alloc");
+        CU(cudaMemsetAsync(c->stats.p, 0, sizeof(unsigned long long) * B2R_STAT_COUNT, c->stream), "stats clear");
+    }
+    return B2R_OK;
+}
+
+int b2r_get_stats(b2r_ctx* ctx, unsigned long long* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!out) return fail(c, B2R_E_INVALID, "null out");
+    memset(out, 0, sizeof(unsigned long long) * B2R_STAT_COUNT);
+    if (!c->statsOn || !c->stats.p) return B2R_OK;
+    CU(cudaStreamSynchronize(c->stream), "sync");
+    CU(cudaMemcpy(out, c->stats.p, sizeof(unsigned long long) * B2R_STAT_COUNT, cudaMemcpyDeviceToHost), "stats D2H");
+    return B2R_OK;
+}
+
+unsigned long long b2r_launch_count(const b2r_ctx* ctx) {
+    const Ctx* c = reinterpret_cast<const Ctx*>(ctx);
+    return c ? c->launches : 0ull;
+}
+
+int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    double t = 0, s = 0;
+    CU(run_fp32_peak(c, &t, &s), "fp32_peak_kernel");
+    if (tflops) *tflops = t;
+    if (seconds) *seconds = s;
+    return B2R_OK;
+}
+
+// ---- raytracer ------------------------------------------------------------------
+int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    c->lastDraw = 0;
+    if (y1 == y0) return B2R_OK;
+    RtLaunch a;
+    a.geom = c->geom.as<float4>();
+    a.frame = c->frame.as<DevFrame>();
+    a.T = c->T;
+    a.W = c->W;
+    a.H = c->H;
+    a.y0 = y0;
+    a.y1 = y1;
+    a.tilesX = (c->W + 31) / 32;
+    a.numTiles = a.tilesX * ((y1 - y0 + 7) / 8);
+    a.colours = d_col;
+    a.closest = d_clo;
+    a.focal = d_foc;
+    a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
+    a.useFilter = c->optRtFilter;
+    cudaError_t e = launch_rt_trace_shade(c, a, c->stream);
+    if (e == cudaErrorInvalidConfiguration)
+        return fail(c, B2R_E_UNSUPPORTED, "raytracer: triangles x ray origins exceed the shared-memory resident limit of this build");
+    if (e != cudaSuccess) return cuda_fail(c, e, "rt_trace_shade_kernel");
+    return B2R_OK;
+}
+
+static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* clo, float* foc, uint32_t* surface) {
+    if (int rc = check_band(c, y0, y1)) return rc;
+    const size_t n = (size_t)c->W * c->H;
+    CU(c->colours.reserve(n * 12), "alloc pixelColours");
+    if (clo) CU(c->closest.reserve(n * 20), "alloc closestIntersections");
+    const bool needFocal = foc || (surface && c->params.dofEnabled);
+    if (needFocal) CU(c->focal.reserve(n * 4), "alloc focalDistances");
+    if (int rc = b2r_rt_draw_device_async(reinterpret_cast<b2r_ctx*>(c), y0, y1, c->colours.as<float>(),
+                                          clo ? c->closest.as<b2r_intersection>() : nullptr,
+                                          needFocal ? c->focal.as<float>() : nullptr))
+        return rc;
+    if (surface) {
+        CU(c->surface.reserve(n * 4), "alloc surface");
+        CU(launch_resolve_surface(c, y0, y1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+           "resolve_surface_kernel");
+        if (int rc = copy_rows_out(c, surface, c->surface.p, y0, y1, 4)) return rc;
+    }
+    if (int rc = copy_rows_out(c, col, c->colours.p, y0, y1, 12)) return rc;
+    if (int rc = copy_rows_out(c, clo, c->closest.p, y0, y1, 20)) return rc;
+    if (int rc = copy_rows_out(c, foc, c->focal.p, y0, y1, 4)) return rc;
+    CU(cudaStreamSynchronize(c->stream), "raytracer draw");
+    return B2R_OK;
+}
+
+int b2r_rt_draw(b2r_ctx* ctx, int y0, int y1, float* col, b2r_intersection* clo, float* foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    return rt_draw_host(c, y0, y1, col, clo, foc, nullptr);
+}
+
+int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* clo, float* foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    return rt_draw_host(c, 0, c->H, col, clo, foc, surface);
+}
+
+// ---- rasteriser -------------------------------------------------------------------
+int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float* d_col, float* d_foc, int32_t* d_win) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    c->lastDraw = 1;
+    if (y1 == y0) return B2R_OK;
+    RasLaunch a;
+    a.raw = c->raw.as<unsigned char>();
+    a.stride = c->stride;
+    a.culled = c->culled.as<unsigned char>();
+    a.T = c->T;
+    a.frame = c->frame.as<DevFrame>();
+    a.W = c->W;
+    a.H = c->H;
+    a.y0 = y0;
+    a.y1 = y1;
+    a.depth = d_dep;
+    a.colours = d_col;
+    a.focal = d_foc;
+    a.winner = d_win;
+    a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
+    cudaError_t e = launch_ras_draw(c, a, c->stream);
+    if (e == cudaErrorInvalidValue)
+        return fail(c, B2R_E_CAPACITY, "rasteriser: a projected triangle exceeds 2^22 rows or 2^24 pixels in a coordinate "
+                                      "(a vertex at or behind the camera plane); the reference cannot draw it either");
+    if (e != cudaSuccess) return cuda_fail(c, e, "rasteriser kernels");
+    return B2R_OK;
+}
+
+static int ras_draw_host(Ctx* c, int y0, int y1, float* dep, float* col, float* foc, int32_t* win, uint32_t* surface) {
+    if (int rc = check_band(c, y0, y1)) return rc;
+    const size_t n = (size_t)c->W * c->H;
+    CU(c->colours.reserve(n * 12), "alloc pixelColours");
+    if (dep) CU(c->depth.reserve(n * 4), "alloc depthBuffer");
+    if (win) CU(c->winner.reserve(n * 4), "alloc winnerIndex");
+    const bool needFocal = foc || (surface && c->params.dofEnabled);
+    if (needFocal) CU(c->focal.reserve(n * 4), "alloc focalDistances");
+    if (int rc = b2r_ras_draw_device_async(reinterpret_cast<b2r_ctx*>(c), y0, y1, dep ? c->depth.as<float>() : nullptr,
+                                           c->colours.as<float>(), needFocal ? c->focal.as<float>() : nullptr,
+                                           win ? c->winner.as<int32_t>() : nullptr))
+        return rc;
+    if (surface) {
+        CU(c->surface.reserve(n * 4), "alloc surface");
+        CU(launch_resolve_surface(c, y0, y1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+           "resolve_surface_kernel");
+        if (int rc = copy_rows_out(c, surface, c->surface.p, y0, y1, 4)) return rc;
+    }
+    if (int rc = copy_rows_out(c, dep, c->depth.p, y0, y1, 4)) return rc;
+    if (int rc = copy_rows_out(c, col, c->colours.p, y0, y1, 12)) return rc;
+    if (int rc = copy_rows_out(c, foc, c->focal.p, y0, y1, 4)) return rc;
+    if (int rc = copy_rows_out(c, win, c->winner.p, y0, y1, 4)) return rc;
+    CU(cudaStreamSynchronize(c->stream), "rasteriser draw");
+    return B2R_OK;
+}
+
+int b2r_ras_draw(b2r_ctx* ctx, int y0, int y1, float* dep, float* col, float* foc, int32_t* win) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    return ras_draw_host(c, y0, y1, dep, col, foc, win, nullptr);
+}
+
+int b2r_ras_frame(b2r_ctx* ctx, uint32_t* surface, float* dep, float* col, float* foc, int32_t* win) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    return ras_draw_host(c, 0, c->H, dep, col, foc, win, surface);
+}
+
+int b2r_ras_cull(b2r_ctx* ctx, uint8_t* culledOut) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!c->haveScene || !c->haveFrame) return fail(c, B2R_E_NO_SCENE, "b2r_ras_cull needs a scene and frame params");
+    CU(launch_ras_cull(c, c->culled.as<unsigned char>(), c->stream), "ras_cull_kernel");
+    if (culledOut && c->T)
+        CU(cudaMemcpyAsync(culledOut, c->culled.p, (size_t)c->T, cudaMemcpyDeviceToHost, c->stream), "culled D2H");
+    CU(cudaStreamSynchronize(c->stream), "ras_cull");
+    return B2R_OK;
+}
+
+// ---- resolve ----------------------------------------------------------------------
+int b2r_resolve_surface_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_col, const float* d_foc, uint32_t* d_surface) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (y0 < 0 || y1 > c->H || y0 > y1 || !d_col || !d_surface) return fail(c, B2R_E_INVALID, "resolve: bad arguments");
+    if (c->params.dofEnabled && !d_foc) return fail(c, B2R_E_INVALID, "resolve: depth of field needs focalDistances");
+    CU(launch_resolve_surface(c, y0, y1, d_col, d_foc, d_surface, c->stream), "resolve_surface_kernel");
+    return B2R_OK;
+}
+
+int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!surface) return fail(c, B2R_E_INVALID, "null surface");
+    if (c->lastDraw < 0 || !c->colours.p) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
+    const size_t n = (size_t)c->W * c->H;
+    CU(c->surface.reserve(n * 4), "alloc surface");
+    CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+       "resolve_surface_kernel");
+    CU(cudaMemcpyAsync(surface, c->surface.p, n * 4, cudaMemcpyDeviceToHost, c->stream), "surface D2H");
+    CU(cudaStreamSynchronize(c->stream), "resolve");
+    return B2R_OK;
+}
+
+size_t b2r_bmp_payload_bytes(int width, int height) {
+    if (width <= 0 || height <= 0) return 0;
+    return (size_t)((width * 3 + 3) & ~3) * (size_t)height;
+}
+
+int b2r_resolve_bgr8(b2r_ctx* ctx, uint8_t* bgr) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!bgr) return fail(c, B2R_E_INVALID, "null bgr");
+    if (c->lastDraw < 0 || !c->colours.p) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
+    const size_t n = (size_t)c->W * c->H, payload = b2r_bmp_payload_bytes(c->W, c->H);
+    CU(c->surface.reserve(n * 4), "alloc surface");
+    CU(c->bgr.reserve(payload), "alloc bgr");
+    CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+       "resolve_surface_kernel");
+    CU(launch_surface_to_bgr8(c, c->surface.as<uint32_t>(), c->bgr.as<uint8_t>(), c->stream), "surface_to_bgr8_kernel");
+    CU(cudaMemcpyAsync(bgr, c->bgr.p, payload, cudaMemcpyDeviceToHost, c->stream), "bgr D2H");
+    CU(cudaStreamSynchronize(c->stream), "resolve");
+    return B2R_OK;
+}
+
+// Headless SDL_SaveBMP: BITMAPFILEHEADER + BITMAPINFOHEADER (54 bytes), 24 bpp, bottom-up.
+int b2r_write_bmp(const char* path, const uint8_t* payload, int width, int height) {
+    if (!path || !payload || width <= 0 || height <= 0) return B2R_E_INVALID;
+    const uint32_t size = (uint32_t)b2r_bmp_payload_bytes(width, height);
+    unsigned char h[54];
+    memset(h, 0, sizeof h);
+    auto put32 = [&](int off, uint32_t v) { h[off] = v & 0xFF; h[off + 1] = (v >> 8) & 0xFF; h[off + 2] = (v >> 16) & 0xFF; h[off + 3] = (v >> 24) & 0xFF; };
+    h[0] = 'B';
+    h[1] = 'M';
+    put32(2, 54u + size);
+    put32(10, 54u);
+    put32(14, 40u);
+    put32(18, (uint32_t)width);
+    put32(22, (uint32_t)height);
+    h[26] = 1;   // planes
+    h[28] = 24;  // bits per pixel
+    put32(34, size);
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return B2R_E_IO;
+    const bool ok = fwrite(h, 1, 54, fp) == 54 && fwrite(payload, 1, size, fp) == size;
+    return (fclose(fp) == 0 && ok) ? B2R_OK : B2R_E_IO;
+}
+
+}  // extern "C"

@@ -1,0 +1,153 @@
+// b2r_internal.h -- shared between the C-ABI layer (b2r_api.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b2r.h"
+
+namespace b2r {
+
+// ---------------------------------------------------------------------------
+// Per-frame constants, laid out once by b2r_set_frame() on the host (exact
+// reference-order arithmetic where bits matter) and uploaded to HBM in one
+// copy.  Every vec3 is padded to float4 so the kernels can use 128-bit loads.
+// ---------------------------------------------------------------------------
+constexpr int kMaxOrigins = 1 + B2R_RANDOM_POSITIONS;  // camera + every light sample
+
+struct DevFrame {
+    float cam[4];        // cameraPos
+    float R[12];         // cameraRot, column-major, 9 used
+    float Rinv[12];      // glm::inverse(cameraRot) (rasteriser.cpp:559), 9 used
+    float focal;         // focalLength
+    float dofFocal;      // FOCAL_LENGTH
+    float primaryDmax;   // bound on |cameraRot*d|_inf over the frame (filter margin)
+    int   nLights;
+    int   samples;       // shadow samples per light (1 or SOFT_SHADOWS_SAMPLES)
+    int   aaN;           // sub-samples per axis (1 or AA_SAMPLES)
+    int   nOrigins;      // 1 + nLights*samples
+    int   dofEnabled;
+    int   dofKernel;
+    int   pad0[3];
+    float indirect[4];
+    float reflectance[4];
+    float lightPos[B2R_MAX_LIGHTS][4];
+    float lightColor[B2R_MAX_LIGHTS][4];    // color*intensity                 (rasteriser.cpp:577)
+    float lightPower[B2R_MAX_LIGHTS][4];    // (color*intensity)/float(samples) (raytracer.cpp:282,296)
+    float origin[kMaxOrigins][4];           // [0] camera; [1 + k*samples + s] light sample position
+};
+
+// Scene-static per-triangle record for the raytracer: 5 float4 = 80 bytes.
+//   q0 = (v0.x, v0.y, v0.z, e1.x)   q1 = (e1.y, e1.z, e2.x, e2.y)
+//   q2 = (e2.z, n.x, n.y, n.z)      n  = cross(e1,e2)           (raytracer.cpp:216-217,225)
+//   q3 = (nh.x, nh.y, nh.z, col.r)  nh = normalize(normal)      (raytracer.cpp:300)
+//   q4 = (col.g, col.b, 0, 0)
+constexpr int kGeomQuads = 5;
+// Per (ray origin, triangle) record: 5 float4 = 80 bytes.
+//   q0 = (be2.xyz, e1e2b)  q1 = (e1b.xyz, 0)                    (raytracer.cpp:218,226-227,231)
+//   q2..q4 = the three conservative filter forms (see rt_kernels.cu)
+constexpr int kOriginQuads = 5;
+
+struct RtLaunch {
+    const float4* geom;      // T * kGeomQuads
+    const DevFrame* frame;
+    int T;
+    int W, H, y0, y1;
+    int tilesX, numTiles;
+    float* colours;                     // may be null
+    b2r_intersection* closest;          // may be null
+    float* focal;                       // may be null
+    unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
+    int useFilter;
+};
+
+struct RasLaunch {
+    const unsigned char* raw;  // reference Triangle records
+    int stride;                // 60 or 64
+    const unsigned char* culled;  // one byte per triangle (may be null => nothing culled)
+    int T;
+    const DevFrame* frame;
+    int W, H, y0, y1;
+    float* depth;
+    float* colours;
+    float* focal;
+    int32_t* winner;
+    unsigned long long* stats;
+};
+
+struct Ctx;
+
+// kernels (each returns cudaGetLastError() of its launches)
+cudaError_t launch_tri_prep(Ctx* c, cudaStream_t s);
+cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s);
+cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s);
+cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s);
+cudaError_t launch_resolve_surface(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
+                                   uint32_t* d_surface, cudaStream_t s);
+cudaError_t launch_surface_to_bgr8(Ctx* c, const uint32_t* d_surface, uint8_t* d_bgr, cudaStream_t s);
+cudaError_t run_fp32_peak(Ctx* c, double* tflops, double* seconds);
+
+// Growable device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Ctx {
+    int device = 0;
+    int W = 0, H = 0;
+    int smCount = 148;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // scene
+    int T = 0;
+    int stride = 0;
+    DevBuf raw;      // reference Triangle records as given
+    DevBuf culled;   // T bytes
+    DevBuf geom;     // T * 80 bytes (raytracer)
+    bool haveScene = false;
+
+    // frame
+    b2r_frame_params params{};
+    DevFrame hostFrame{};
+    DevFrame* pinnedFrame = nullptr;
+    DevBuf frame;
+    bool haveFrame = false;
+
+    // outputs kept on the device between draw and resolve / host copies
+    DevBuf colours, closest, focal, depth, winner, surface, bgr;
+    // rasteriser intermediates
+    DevBuf rasTri, rasRows, rasKeys, rasScratch;
+    // pinned staging for host-pointer entry points
+    void* pinned = nullptr;
+    size_t pinnedCap = 0;
+
+    DevBuf stats;
+    bool statsOn = false;
+    unsigned long long hostStats[B2R_STAT_COUNT] = {0};
+    unsigned long long launches = 0;
+    int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0;
+    int lastDraw = -1;  // 0 raytracer, 1 rasteriser
+};
+
+}  // namespace b2r

@@ -1,0 +1,538 @@
+// ras_kernels.cu -- the rasteriser hot path on sm_100a.
+//
+// Replaces Draw() -> DrawPolygon() -> VertexShader / ComputePolygonRows /
+// Interpolate / DrawRows / DrawLineSDL / Bresenham / PixelShader of
+// rasteriser/Source/rasteriser.cpp:461-482, :532-546, :549-589, :592-672,
+// :674-768, and the culling block of Update() (:385-447).
+//
+// The reference draws triangles serially in index order with a strict
+// `zinv > depthBuffer` test against a buffer cleared to 0 (:606, :188).  The
+// final image therefore only depends on, per pixel, the fragment with the
+// largest zinv, the lowest triangle index among exact ties, and only
+// fragments with zinv > 0.  A 64-bit key (zinv bits << 32 | ~index) and an
+// atomicMax reproduce that for any execution order; shading is deferred to
+// the winner (PixelShader's writes are simply overwritten by later winners in
+// the reference, so shading only the final one gives identical arrays).
+//
+// Stages (all arithmetic in reference order, non-fused):
+//   ras_setup     1 thread / triangle: VertexShader x3, minY, ROWS, edge sample counts
+//   scan          exclusive prefix sums (rows, edge samples) -> buffer offsets
+//   ras_edges     1 thread / (triangle, edge): Interpolate's serial float
+//                 accumulation, replayed step by step (it decides coverage via
+//                 int(current.x) and the zinv values the depth test compares)
+//   ras_rows      1 warp / 32 polygon rows: left/right resolve with the
+//                 reference's strict < / > rules in edge order, then the row's
+//                 fragments -> atomicMax on the key buffer; short rows per lane,
+//                 long rows cooperatively across the warp
+//   ras_shade     1 thread / pixel: winner's attributes recomputed from its row
+//                 record, PixelShader, outputs
+#include <limits.h>
+
+#include "b2r_internal.h"
+#include "exact.cuh"
+
+namespace b2r {
+
+// (int)float with x86 cvttss2si semantics (out of range / NaN -> INT_MIN), which is
+// what the reference's int(...) conversions do on the CPU it was built for.
+__device__ __forceinline__ int f2i_x86(float f) {
+    return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
+}
+
+struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
+    int x, y;
+    float zinv;
+    V3 p;
+};
+
+struct TriSetup {  // 24 words
+    int vx[3], vy[3];
+    float vz[3];
+    float vp[9];
+    int minY, rows;
+    unsigned rowBase, sampleBase;
+    int drawn, pad;
+};
+
+struct EdgeSample {  // 5 words
+    int x;
+    float zinv;
+    float p[3];
+};
+
+struct RowRec {  // 12 words: left/right ends of one polygon row (y implied)
+    int lx, rx;
+    float lz, rz;
+    float lp[3], rp[3];
+    int pad[2];
+};
+
+constexpr int kMaxRowsPerTriangle = 1 << 22;
+constexpr int kCoordLimit = 1 << 24;
+
+__device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, int H) {
+    RPixel p;
+    V3 pos = xvec_mat(xsub3(v, mk3(f->cam[0], f->cam[1], f->cam[2])), f->R);  // :535
+    p.p = xdivs3(pos, pos.z);                                                   // :538
+    p.zinv = xdiv(1.0f, pos.z);                                                 // :541
+    float fx = xmul(f->focal, xmul(pos.x, p.zinv));
+    float fy = xmul(f->focal, xmul(pos.y, p.zinv));
+    p.x = f2i_x86(xadd(__int2float_rn(f2i_x86(fx)), xdiv((float)W, 2.0f)));    // :544
+    p.y = f2i_x86(xadd(__int2float_rn(f2i_x86(fy)), xdiv((float)H, 2.0f)));    // :545
+    return p;
+}
+
+// ---- stage 1 ---------------------------------------------------------------
+__global__ void ras_setup_kernel(RasLaunch a, TriSetup* __restrict__ ts, uint2* __restrict__ counts,
+                                 unsigned* __restrict__ err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.T) return;
+    uint2 cnt = make_uint2(0u, 0u);
+    TriSetup s;
+    s.drawn = 0;
+    s.rows = 0;
+    s.minY = 0;
+    s.rowBase = s.sampleBase = 0;
+    s.pad = 0;
+    bool culled = a.culled && a.culled[i];
+    if (!culled) {
+        const float* t = reinterpret_cast<const float*>(a.raw + (size_t)i * a.stride);
+        int maxY = INT_MIN, minY = INT_MAX;
+        bool bad = false;
+        for (int k = 0; k < 3; ++k) {
+            RPixel p = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);
+            s.vx[k] = p.x;
+            s.vy[k] = p.y;
+            s.vz[k] = p.zinv;
+            s.vp[3 * k] = p.p.x;
+            s.vp[3 * k + 1] = p.p.y;
+            s.vp[3 * k + 2] = p.p.z;
+            maxY = max(maxY, p.y);
+            minY = min(minY, p.y);
+            bad = bad || p.x <= -kCoordLimit || p.x >= kCoordLimit || p.y <= -kCoordLimit || p.y >= kCoordLimit;
+        }
+        if (bad || (maxY - minY + 1) > kMaxRowsPerTriangle) {
+            atomicExch(err, 1u);  // the reference would try to allocate/walk an absurd row count
+        } else {
+            s.drawn = 1;
+            s.minY = minY;
+            s.rows = maxY - minY + 1;  // :682
+            cnt.x = (unsigned)s.rows;
+            cnt.y = (unsigned)(abs(s.vy[0] - s.vy[1]) + abs(s.vy[1] - s.vy[2]) + abs(s.vy[2] - s.vy[0]) + 3);  // :712
+        }
+    }
+    ts[i] = s;
+    counts[i] = cnt;
+}
+
+// ---- exclusive scan of uint2 (three small kernels) ---------------------------
+constexpr int kScanBlock = 1024;
+
+__device__ __forceinline__ uint2 add2(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
+
+__device__ uint2 block_exclusive_scan(uint2 v, uint2* total) {
+    __shared__ uint2 warpSums[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 inc = v;
+    for (int off = 1; off < 32; off <<= 1) {
+        unsigned x = __shfl_up_sync(0xffffffffu, inc.x, off), y = __shfl_up_sync(0xffffffffu, inc.y, off);
+        if (lane >= off) inc = add2(inc, make_uint2(x, y));
+    }
+    if (lane == 31) warpSums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint2 w = (lane < (int)(blockDim.x >> 5)) ? warpSums[lane] : make_uint2(0u, 0u);
+        uint2 winc = w;
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned x = __shfl_up_sync(0xffffffffu, winc.x, off), y = __shfl_up_sync(0xffffffffu, winc.y, off);
+            if (lane >= off) winc = add2(winc, make_uint2(x, y));
+        }
+        warpSums[lane] = make_uint2(winc.x - w.x, winc.y - w.y);  // exclusive
+        if (lane == 31) *total = winc;
+    }
+    __syncthreads();
+    uint2 base = warpSums[warp];
+    __syncthreads();
+    return make_uint2(base.x + inc.x - v.x, base.y + inc.y - v.y);
+}
+
+__global__ void scan_blocks_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, uint2* __restrict__ blockSums, int n) {
+    __shared__ uint2 total;
+    int i = blockIdx.x * kScanBlock + threadIdx.x;
+    uint2 v = (i < n) ? in[i] : make_uint2(0u, 0u);
+    uint2 ex = block_exclusive_scan(v, &total);
+    if (i < n) out[i] = ex;
+    if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
+}
+
+// one block: exclusive scan of the block sums in place; totals[0] = grand total
+__global__ void scan_sums_kernel(uint2* __restrict__ blockSums, int nBlocks, uint2* __restrict__ totals) {
+    __shared__ uint2 total;
+    uint2 carry = make_uint2(0u, 0u);
+    for (int base = 0; base < nBlocks; base += kScanBlock) {
+        int i = base + threadIdx.x;
+        uint2 v = (i < nBlocks) ? blockSums[i] : make_uint2(0u, 0u);
+        uint2 ex = block_exclusive_scan(v, &total);
+        if (i < nBlocks) blockSums[i] = add2(ex, carry);
+        carry = add2(carry, total);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) totals[0] = carry;
+}
+
+__global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __restrict__ blockSums,
+                                  TriSetup* __restrict__ ts, int n) {
+    int i = blockIdx.x * kScanBlock + threadIdx.x;
+    if (i >= n) return;
+    uint2 o = add2(ex[i], blockSums[blockIdx.x]);
+    ts[i].rowBase = o.x;
+    ts[i].sampleBase = o.y;
+}
+
+// ---- stage 2: Interpolate (:615-637), one thread per (triangle, edge) --------
+__global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T, EdgeSample* __restrict__ samples,
+                                 unsigned* __restrict__ rowOwner) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = gid / 3, e = gid - 3 * i;
+    if (i >= T) return;
+    const TriSetup s = ts[i];
+    if (!s.drawn) return;
+    if (e == 0)
+        for (int r = 0; r < s.rows; ++r) rowOwner[s.rowBase + r] = (unsigned)i;
+    const int j = (e + 1) % 3;  // :707
+    const int n = abs(s.vy[e] - s.vy[j]) + 1;  // :712
+    unsigned off = s.sampleBase;
+    for (int k = 0; k < e; ++k) off += (unsigned)(abs(s.vy[k] - s.vy[(k + 1) % 3]) + 1);
+    const float div = (float)max(n - 1, 1);  // :622
+    // Pixel operator- (TestModel.h:82-85) then fPixel operator/ (:124-127)
+    const float sx = xdiv((float)(s.vx[j] - s.vx[e]), div);
+    const float sz = xdiv(xsub(s.vz[j], s.vz[e]), div);
+    const V3 a3 = mk3(s.vp[3 * e], s.vp[3 * e + 1], s.vp[3 * e + 2]);
+    const V3 b3 = mk3(s.vp[3 * j], s.vp[3 * j + 1], s.vp[3 * j + 2]);
+    const V3 sp = xdivs3(xsub3(b3, a3), div);
+    float cx = (float)s.vx[e], cz = s.vz[e];  // fPixel(Pixel&)
+    V3 cp = a3;
+    EdgeSample* out = samples + off;
+    for (int k = 0; k < n; ++k) {  // :626-636 -- serial float accumulation, order matters
+        EdgeSample q;
+        q.x = f2i_x86(cx);
+        q.zinv = cz;
+        q.p[0] = cp.x;
+        q.p[1] = cp.y;
+        q.p[2] = cp.z;
+        out[k] = q;
+        cx = xadd(cx, sx);
+        cz = xadd(cz, sz);
+        cp = xadd3(cp, sp);
+    }
+}
+
+// ---- stage 3: ComputePolygonRows' per-row resolve (:716-733) + DrawRows/DrawLineSDL/Bresenham ----
+__device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSample* __restrict__ samples, int y) {
+    RowRec r;
+    r.lx = INT_MAX;    // :696
+    r.rx = -INT_MAX;   // :697
+    r.lz = r.rz = 0.f;
+    r.lp[0] = r.lp[1] = r.lp[2] = r.rp[0] = r.rp[1] = r.rp[2] = 0.f;
+    r.pad[0] = r.pad[1] = 0;
+    unsigned off = s.sampleBase;
+    for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
+        const int j = (e + 1) % 3;
+        const int ya = s.vy[e], yb = s.vy[j];
+        const int n = abs(ya - yb) + 1;
+        if (y >= min(ya, yb) && y <= max(ya, yb)) {
+            const EdgeSample q = samples[off + (unsigned)abs(y - ya)];
+            if (q.x < r.lx) {  // :718 strict: the first edge to reach an extreme keeps its attributes
+                r.lx = q.x;
+                r.lz = q.zinv;
+                r.lp[0] = q.p[0]; r.lp[1] = q.p[1]; r.lp[2] = q.p[2];
+            }
+            if (q.x > r.rx) {  // :726
+                r.rx = q.x;
+                r.rz = q.zinv;
+                r.rp[0] = q.p[0]; r.rp[1] = q.p[1]; r.rp[2] = q.p[2];
+            }
+        }
+        off += (unsigned)n;
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri) {
+    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(0xFFFFFFFFu - tri);
+}
+
+// fragments i in [i0,i1) of one row; Bresenham with dy == 0 (:639-672): x = lx+1+i, zinv = lz + zstep*float(i)
+__device__ __forceinline__ void raster_span(unsigned long long* __restrict__ keyRow, int lx, float lz, float zstep,
+                                            unsigned tri, int i0, int i1, int istride) {
+    for (int i = i0; i < i1; i += istride) {
+        const float zinv = xadd(lz, xmul(zstep, (float)i));  // :667
+        if (zinv > 0.0f)                                     // :606 against a buffer cleared to 0 (:188)
+            atomicMax(keyRow + (lx + 1 + i), pack_key(zinv, tri));
+    }
+}
+
+constexpr int kShortRow = 8;
+
+__global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restrict__ ts,
+                                                       const EdgeSample* __restrict__ samples,
+                                                       const unsigned* __restrict__ rowOwner, unsigned nRows,
+                                                       RowRec* __restrict__ rows,
+                                                       unsigned long long* __restrict__ keys, int W, int y0,
+                                                       int y1, unsigned long long* __restrict__ stats) {
+    const unsigned rid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int lx = 0, pixels = 0, i0 = 0, i1 = 0, y = 0;
+    float lz = 0.f, zstep = 0.f;
+    unsigned tri = 0;
+    if (rid < nRows) {
+        tri = rowOwner[rid];
+        const TriSetup s = ts[tri];
+        y = s.minY + (int)(rid - s.rowBase);
+        // DrawRows (:743): rows with y outside the screen are skipped; outside the band: another GPU's
+        if (y >= y0 && y < y1) {
+            RowRec r = resolve_row(s, samples, y);
+            rows[rid] = r;
+            lx = r.lx;
+            lz = r.lz;
+            pixels = r.rx - r.lx;                              // :598
+            zstep = xdiv(xsub(r.rz, r.lz), (float)pixels);     // :648
+            i0 = max(0, -lx - 1);                              // :663 x >= 0
+            i1 = min(pixels, W - lx - 1);                      //      x <  W
+            if (i1 < i0) i1 = i0;
+        }
+    }
+    const int count = i1 - i0;
+    if (stats) {
+        unsigned long long c = (unsigned long long)count;
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (lane == 0 && c) atomicAdd(stats + B2R_STAT_RAS_DEPTH_TESTS, c);
+    }
+    unsigned long long* keyRow = keys + (size_t)(y - y0) * (size_t)W;
+    // short rows: each lane walks its own; long rows: the whole warp walks them one at a time
+    const bool isLong = count > kShortRow;
+    if (count > 0 && !isLong) raster_span(keyRow, lx, lz, zstep, tri, i0, i1, 1);
+    unsigned longMask = __ballot_sync(0xffffffffu, isLong);
+    while (longMask) {
+        const int src = __ffs(longMask) - 1;
+        longMask &= longMask - 1;
+        const int blx = __shfl_sync(0xffffffffu, lx, src);
+        const float blz = __shfl_sync(0xffffffffu, lz, src);
+        const float bzs = __shfl_sync(0xffffffffu, zstep, src);
+        const unsigned btri = __shfl_sync(0xffffffffu, tri, src);
+        const int bi0 = __shfl_sync(0xffffffffu, i0, src), bi1 = __shfl_sync(0xffffffffu, i1, src);
+        const int by = __shfl_sync(0xffffffffu, y, src);
+        raster_span(keys + (size_t)(by - y0) * (size_t)W, blx, blz, bzs, btri, bi0 + lane, bi1, 32);
+    }
+}
+
+// ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------
+__global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ ts,
+                                                        const RowRec* __restrict__ rows,
+                                                        const unsigned long long* __restrict__ keys) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = a.y0 + blockIdx.y;
+    if (x >= a.W || y >= a.y1) return;
+    const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
+    const unsigned long long key = keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x];
+    float depth = 0.f, focal = 0.f;
+    V3 colour = mk3(0.f, 0.f, 0.f);
+    int winner = -1;
+    if (key != 0ull) {
+        const DevFrame* __restrict__ f = a.frame;
+        const unsigned tri = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
+        winner = (int)tri;
+        const TriSetup* s = ts + tri;
+        const RowRec r = rows[s->rowBase + (unsigned)(y - s->minY)];
+        const int pixels = r.rx - r.lx;
+        const float fi = (float)(x - r.lx - 1);
+        const float fdx = (float)pixels;
+        const float zinv = xadd(r.lz, xmul(xdiv(xsub(r.rz, r.lz), fdx), fi));                    // :648,667
+        const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
+        const V3 pos3d = xadd3(lp, xscale3(xdivs3(xsub3(rp, lp), fdx), fi));                     // :649,668
+        depth = zinv;  // == the key's high word
+        const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
+        const V3 normal = mk3(t[9], t[10], t[11]), color = mk3(t[12], t[13], t[14]);
+        const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
+        V3 P = xdivs3(pos3d, zinv);        // :557
+        P = xvec_mat(P, f->Rinv);          // :559
+        P = xadd3(P, cam);                 // :560
+        const V3 dc = xsub3(cam, P);       // glm::distance(pPos3d, cameraPos) = length(cameraPos - pPos3d)
+        focal = xsub(xsqrt(xdot3(dc, dc)), f->dofFocal);  // :564-565
+        V3 result = mk3(0.f, 0.f, 0.f);
+        for (int k = 0; k < f->nLights; ++k) {  // :567-584
+            const V3 L = mk3(f->lightPos[k][0], f->lightPos[k][1], f->lightPos[k][2]);
+            const V3 dl = xsub3(L, P);
+            const float r2 = xdot3(dl, dl);
+            const float rr = xsqrt(r2);                        // :575
+            const float A = sphere_area(rr);                   // :576
+            const V3 lc = mk3(f->lightColor[k][0], f->lightColor[k][1], f->lightColor[k][2]);  // :577
+            const V3 rDir = xscale3(dl, xdiv(1.0f, rr));       // :578
+            const V3 B = xdivs3(lc, A);                        // :580
+            const V3 D = xscale3(B, std_max(xdot3(rDir, normal), 0.0f));  // :582 (normal not re-normalised)
+            result = xadd3(result, D);
+        }
+        const V3 refl = mk3(f->reflectance[0], f->reflectance[1], f->reflectance[2]);
+        const V3 ind = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
+        colour = xmul3(xmul3(refl, xadd3(result, ind)), color);  // :587
+    }
+    if (a.depth) a.depth[idx] = depth;
+    if (a.colours) {
+        a.colours[3 * idx] = colour.x;
+        a.colours[3 * idx + 1] = colour.y;
+        a.colours[3 * idx + 2] = colour.z;
+    }
+    if (a.focal) a.focal[idx] = focal;
+    if (a.winner) a.winner[idx] = winner;
+}
+
+__global__ void ras_count_kernel(const TriSetup* __restrict__ ts, int T, unsigned long long* __restrict__ stats) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long d = 0, r = 0;
+    if (i < T && ts[i].drawn) {
+        d = 1;
+        r = (unsigned long long)ts[i].rows;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, off);
+        r += __shfl_xor_sync(0xffffffffu, r, off);
+    }
+    if ((threadIdx.x & 31) == 0 && d) {
+        atomicAdd(stats + B2R_STAT_RAS_TRIANGLES, d);
+        atomicAdd(stats + B2R_STAT_RAS_ROWS, r);
+    }
+}
+
+// ---- culling block of Update() (:385-447) ------------------------------------
+struct CullConsts {
+    float m00, m11, m22, m32;
+};
+
+__global__ void ras_cull_kernel(const unsigned char* __restrict__ raw, int stride, int T, const DevFrame* __restrict__ f,
+                                CullConsts cc, int backface, int frustum, unsigned char* __restrict__ culled) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const float* t = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
+    int cull = 0;
+    if (backface) {  // :408-414
+        if (xdot3(xsub3(mk3(t[0], t[1], t[2]), cam), mk3(t[9], t[10], t[11])) > 0.0f) cull = 1;
+    }
+    if (frustum && !cull) {  // :416-446
+        bool anyInside = false;
+        for (int k = 0; k < 3; ++k) {
+            const V3 v = xvec_mat(xsub3(mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), cam), f->R);  // :423-425
+            // vec4(v,1) * transform, all sixteen terms of glm/detail/type_mat4x4.inl:664-675
+            const float v3 = 1.0f, z0 = 0.0f;
+            float X = xadd(xadd(xadd(xmul(cc.m00, v.x), xmul(z0, v.y)), xmul(z0, v.z)), xmul(z0, v3));
+            float Y = xadd(xadd(xadd(xmul(z0, v.x), xmul(cc.m11, v.y)), xmul(z0, v.z)), xmul(z0, v3));
+            float Z = xadd(xadd(xadd(xmul(z0, v.x), xmul(z0, v.y)), xmul(cc.m22, v.z)), xmul(z0, v3));
+            float Wc = xadd(xadd(xadd(xmul(z0, v.x), xmul(z0, v.y)), xmul(cc.m32, v.z)), xmul(z0, v3));
+            X = xdiv(X, Wc);  // :435-437
+            Y = xdiv(Y, Wc);
+            Z = xdiv(Z, Wc);
+            anyInside = anyInside || (X >= -1.0f && X <= 1.0f && Y >= -1.0f && Y <= 1.0f && Z >= 0.0f && Z <= 1.0f);  // :453
+        }
+        if (!anyInside) cull = 1;  // :444-445
+    }
+    culled[i] = (unsigned char)cull;
+}
+
+// ---- host side ------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s) {
+    // Frame constants of :385-402, evaluated on the host in reference order (float, libm acosf/tanf like the
+    // reference's cos/sin/acos/tan calls -- none of it is per-triangle work).
+    const b2r_frame_params& p = c->params;
+    V3 fv = xnormalize3(xvec_mat(mk3(0.f, 0.f, 1.0f), p.cameraRot));                    // :385
+    float nearZ = xadd(p.cameraPos[2], xmul(fv.z, 0.1f)), farZ = xadd(p.cameraPos[2], xmul(fv.z, 15.0f));  // :386
+    float w = (float)c->W, h = (float)c->H;
+    V3 tv = mk3(0.0f, -h / 2.0f, p.focalLength), bv = mk3(0.0f, h / 2.0f, p.focalLength);  // :392-393
+    float cy = xdot3(tv, bv) / (xsqrt(xdot3(tv, tv)) * xsqrt(xdot3(bv, bv)));           // :394
+    float rfovy = acosf(cy);                                                            // :395
+    float aspect = w / h;
+    CullConsts cc;
+    cc.m00 = (1.0f / tanf(rfovy / 2.0f)) / aspect;  // :398
+    cc.m11 = (1.0f / tanf(rfovy / 2.0f));           // :399
+    cc.m22 = farZ / (farZ - nearZ);                 // :400
+    cc.m32 = 1.0f;                                  // :401-402
+    if (c->T == 0) return cudaSuccess;
+    ras_cull_kernel<<<(c->T + 255) / 256, 256, 0, s>>>(c->raw.as<unsigned char>(), c->stride, c->T,
+                                                       c->frame.as<DevFrame>(), cc, p.backfaceCulling,
+                                                       p.frustumCulling, d_culled);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
+cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
+    const int T = a.T;
+    const int bandH = a.y1 - a.y0;
+    cudaError_t e;
+    // scratch layout: [counts uint2 x T][excl uint2 x T][blockSums uint2 x nb][totals uint2][err u32]
+    const int nb = (T + kScanBlock - 1) / kScanBlock;
+    const size_t offCounts = 0, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
+                 offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
+                 offTotals = align_up(offSums + sizeof(uint2) * (size_t)(nb + 1), 256), offErr = offTotals + 64,
+                 scratchBytes = offErr + 64;
+    if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
+    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1))) != cudaSuccess) return e;
+    if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
+    unsigned char* sc = c->rasScratch.as<unsigned char>();
+    uint2* counts = reinterpret_cast<uint2*>(sc + offCounts);
+    uint2* excl = reinterpret_cast<uint2*>(sc + offExcl);
+    uint2* sums = reinterpret_cast<uint2*>(sc + offSums);
+    uint2* totals = reinterpret_cast<uint2*>(sc + offTotals);
+    unsigned* err = reinterpret_cast<unsigned*>(sc + offErr);
+    TriSetup* ts = c->rasTri.as<TriSetup>();
+    unsigned long long* keys = c->rasKeys.as<unsigned long long>();
+
+    if ((e = cudaMemsetAsync(totals, 0, 128, s)) != cudaSuccess) return e;  // totals + err
+    if ((e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)bandH * a.W, s)) != cudaSuccess) return e;  // depthBuffer = 0 (:188)
+    uint2 hostTotals = make_uint2(0u, 0u);
+    unsigned hostErr = 0;
+    if (T > 0) {
+        ras_setup_kernel<<<(T + 255) / 256, 256, 0, s>>>(a, ts, counts, err);
+        scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, T);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
+        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, T);
+        c->launches += 4;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        // buffer sizes depend on the projected geometry: read the two totals back (8 bytes)
+        if ((e = cudaMemcpyAsync(c->pinned, totals, sizeof(uint2), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync((char*)c->pinned + 16, err, sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+        hostTotals = *reinterpret_cast<uint2*>(c->pinned);
+        hostErr = *reinterpret_cast<unsigned*>((char*)c->pinned + 16);
+        if (hostErr) return cudaErrorInvalidValue;
+    }
+    const unsigned nRows = hostTotals.x, nSamples = hostTotals.y;
+    if (nRows > 0) {
+        if ((e = c->rasRows.reserve(sizeof(RowRec) * (size_t)nRows + sizeof(unsigned) * (size_t)nRows +
+                                    sizeof(EdgeSample) * (size_t)nSamples + 1024)) != cudaSuccess)
+            return e;
+        unsigned char* rb = c->rasRows.as<unsigned char>();
+        RowRec* rows = reinterpret_cast<RowRec*>(rb);
+        unsigned* owner = reinterpret_cast<unsigned*>(rb + align_up(sizeof(RowRec) * (size_t)nRows, 256));
+        EdgeSample* samples = reinterpret_cast<EdgeSample*>(reinterpret_cast<unsigned char*>(owner) +
+                                                            align_up(sizeof(unsigned) * (size_t)nRows, 256));
+        ras_edges_kernel<<<(3 * T + 127) / 128, 128, 0, s>>>(ts, T, samples, owner);
+        ras_rows_kernel<<<(nRows + 255) / 256, 256, 0, s>>>(ts, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1,
+                                                           a.stats);
+        c->launches += 2;
+        if (a.stats) {
+            ras_count_kernel<<<(T + 255) / 256, 256, 0, s>>>(ts, T, a.stats);
+            c->launches++;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    {
+        dim3 grid((a.W + 255) / 256, bandH);
+        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, c->rasRows.as<RowRec>(), keys);
+        c->launches++;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace b2r

@@ -1,0 +1,137 @@
+// resolve_kernels.cu -- the frame tail both reference programs share:
+//   CalculateDOF()   raytracer.cpp:608-656 == rasteriser.cpp:484-529
+//   PutPixelSDL()    SDLauxiliary.h:70-81  (Uint8(clamp(255*c, 0, 255)), truncation)
+// and the 24-bit bottom-up payload SDL_SaveBMP writes (raytracer.cpp:175).
+// One thread per pixel; HBM-bound (12-16 B read, 4 B written per pixel).
+// Also: the FP32 FFMA throughput microbenchmark that gives the raytracer's
+// roofline denominator (MEASURED_PEAKS.json has no FP32 entry).
+#include "b2r_internal.h"
+#include "exact.cuh"
+
+namespace b2r {
+
+__device__ __forceinline__ uint32_t quantise(float c) {
+    float v = xmul(255.0f, c);        // 255*color.r
+    v = (v < 0.f) ? 0.f : v;          // glm::clamp = min(max(x, 0), 255)
+    v = (255.f < v) ? 255.f : v;
+    return __float2uint_rz(v) & 0xFFu;  // Uint8(...)
+}
+
+// Out-of-range policy for the DOF window (the reference reads without bounds checks,
+// raytracer.cpp:637): the flattened index is used as-is inside [0, W*H) (columns wrap into
+// the neighbouring row exactly like the reference) and contributes 0 outside the array.
+__global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __restrict__ colours,
+                                                              const float* __restrict__ focal, int W, int H,
+                                                              int y0, int dof, int K,
+                                                              uint32_t* __restrict__ surface) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = y0 + blockIdx.y;
+    if (x >= W) return;
+    uint32_t out = 0u;  // the 1-pixel border is never written by the reference: stays black
+    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+        const long long c = (long long)y * W + x;
+        float fr = 0.f, fg = 0.f, fb = 0.f;
+        if (dof) {
+            const float totalPixels = (float)(K * K);                       // :614
+            const int zlo = (int)ceilf(K / -2.0f), zhi = (int)ceilf(K / 2.0f);  // :626
+            const float a = fabsf(focal[c]);
+            const float m = (1.0f < a) ? 1.0f : a;                          // std::min(abs(fd), 1.0f)
+            const float wCentre = xsub(1.0f, xmul(m, xdiv(xsub(totalPixels, 1.0f), totalPixels)));  // :632
+            const float wOther = xmul(m, xdiv(1.0f, totalPixels));                                   // :634
+            const long long n = (long long)W * H;
+            for (int z = zlo; z < zhi; ++z)
+                for (int z2 = zlo; z2 < zhi; ++z2) {
+                    const float wgt = (z == 0 && z2 == 0) ? wCentre : wOther;
+                    const long long q = (long long)(y + z) * W + (x + z2);
+                    if (q < 0 || q >= n) continue;
+                    fr = xadd(fr, xmul(colours[3 * q], wgt));               // :637
+                    fg = xadd(fg, xmul(colours[3 * q + 1], wgt));
+                    fb = xadd(fb, xmul(colours[3 * q + 2], wgt));
+                }
+        } else {
+            fr = colours[3 * c];                                            // :643
+            fg = colours[3 * c + 1];
+            fb = colours[3 * c + 2];
+        }
+        out = (quantise(fr) << 16) | (quantise(fg) << 8) | quantise(fb);    // SDL_MapRGB on XRGB8888
+    }
+    surface[(size_t)y * W + x] = out;
+}
+
+cudaError_t launch_resolve_surface(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
+                                   uint32_t* d_surface, cudaStream_t s) {
+    if (y1 <= y0) return cudaSuccess;
+    dim3 grid((c->W + 255) / 256, y1 - y0);
+    resolve_surface_kernel<<<grid, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0,
+                                                c->params.dofEnabled ? 1 : 0, c->params.dofKernelSize, d_surface);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// XRGB surface -> bottom-up BGR rows padded to 4 bytes.
+__global__ void __launch_bounds__(256) surface_to_bgr8_kernel(const uint32_t* __restrict__ surface, int W, int H,
+                                                              int pitch, uint8_t* __restrict__ bgr) {
+    const int xb = blockIdx.x * blockDim.x + threadIdx.x;  // byte column within the padded row
+    const int y = blockIdx.y;
+    if (xb >= pitch) return;
+    uint8_t v = 0;
+    const int x = xb / 3, ch = xb - 3 * x;
+    if (x < W) v = (uint8_t)((surface[(size_t)y * W + x] >> (8 * ch)) & 0xFFu);  // ch 0 = B, 1 = G, 2 = R
+    bgr[(size_t)(H - 1 - y) * pitch + xb] = v;
+}
+
+cudaError_t launch_surface_to_bgr8(Ctx* c, const uint32_t* d_surface, uint8_t* d_bgr, cudaStream_t s) {
+    const int pitch = (c->W * 3 + 3) & ~3;
+    dim3 grid((pitch + 255) / 256, c->H);
+    surface_to_bgr8_kernel<<<grid, 256, 0, s>>>(d_surface, c->W, c->H, pitch, d_bgr);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ---- FP32 peak: 8 independent FFMA chains per thread --------------------------
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true; keeps the chains alive
+}
+
+cudaError_t run_fp32_peak(Ctx* c, double* tflops, double* seconds) {
+    cudaError_t e;
+    if ((e = c->rasScratch.reserve(1 << 20)) != cudaSuccess) return e;
+    const int blocks = c->smCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    double best = 0.0, bestSec = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(ev0, c->stream);
+        fp32_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->rasScratch.as<float>(), iters, 0.999f, 0.001f);
+        cudaEventRecord(ev1, c->stream);
+        if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        double tf = flops / ((double)ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) {
+            best = tf;
+            bestSec = (double)ms * 1e-3;
+        }
+        c->launches++;
+    }
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (e != cudaSuccess) return e;
+    *tflops = best;
+    *seconds = bestSec;
+    return cudaGetLastError();
+}
+
+}  // namespace b2r

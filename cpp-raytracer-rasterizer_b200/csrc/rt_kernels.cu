@@ -1,0 +1,436 @@
+// rt_kernels.cu -- the raytracer hot path on sm_100a.
+//
+// Replaces Draw() -> ClosestIntersection() -> DirectLight() of
+// raytracer/Source/raytracer.cpp:547-606, :202-257, :265-327 (one thread per
+// pixel, the N x N sub-samples looped in-thread because the reference carries
+// state from one sub-sample to the next, SURVEY.md 8a-1 quirks ii/iii).
+//
+// Structure of one CTA (256 threads, a 32x8 pixel tile per iteration,
+// persistent over tiles):
+//   1. TMA bulk copy (cp.async.bulk + mbarrier) of the scene-static triangle
+//      records (v0, e1, e2, e1 x e2, normalised normal, colour; float4 rows)
+//      from HBM into shared memory.
+//   2. Per (ray origin, triangle) constants computed once per CTA into shared
+//      memory: everything in ClosestIntersection that depends only on `start`
+//      (b, b x e2, e1 x b, (e1 x e2).b -- raytracer.cpp:218,226-227,231) in
+//      reference operation order, plus three conservative filter forms.
+//      Origin 0 is the camera, origins 1.. are the light sample positions the
+//      shadow rays start from (raytracer.cpp:284-291,310).
+//   3. Per ray and triangle: the FMA filter rejects pairs the reference is
+//      CERTAIN to reject; every other pair runs the reference's arithmetic
+//      literally (non-fused mul/add, IEEE div/sqrt), so accepted hits, the
+//      closest-hit index, positions and distances carry the reference's bits.
+//
+// The filter (see setup_origin_triangle): with s = sign((e1 x e2).b), the
+// reference accepts only if s*d1 >= 0, s*d2 >= 0 and s*(d0-d1-d2) >= 0 up to
+// rounding, where d0,d1,d2 are its three dot products with -dir
+// (raytracer.cpp:232-234).  Each is linear in dir, so it is evaluated with
+// two or three FMAs from pre-scaled coefficients and compared against a
+// margin that is >= 4x the worst-case rounding error of BOTH evaluations.
+// A pair is skipped only when one form is below -margin; ties, grazing rays,
+// degenerate triangles and non-finite values all fall through to the exact
+// path.  Switch the filter off with B2R_OPT_RT_FILTER=0: results are
+// identical (tests/test_rt_parity.py checks this).
+#include <float.h>
+
+#include "b2r_internal.h"
+#include "exact.cuh"
+
+namespace b2r {
+
+// ---------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk async copy (TMA), sm_90+/sm_100a.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Scene-static triangle records (once per b2r_set_triangles).
+// ---------------------------------------------------------------------------
+__global__ void tri_prep_kernel(const unsigned char* __restrict__ raw, int stride, int n,
+                                float4* __restrict__ geom) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    V3 v0 = mk3(t[0], t[1], t[2]), v1 = mk3(t[3], t[4], t[5]), v2 = mk3(t[6], t[7], t[8]);
+    V3 nrm = mk3(t[9], t[10], t[11]), col = mk3(t[12], t[13], t[14]);
+    V3 e1 = xsub3(v1, v0);      // raytracer.cpp:216
+    V3 e2 = xsub3(v2, v0);      // :217
+    V3 nn = xcross3(e1, e2);    // :225
+    V3 nh = xnormalize3(nrm);   // :300 (re-normalised on every DirectLight call in the reference)
+    float4* g = geom + (size_t)i * kGeomQuads;
+    g[0] = make_float4(v0.x, v0.y, v0.z, e1.x);
+    g[1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    g[2] = make_float4(e2.z, nn.x, nn.y, nn.z);
+    g[3] = make_float4(nh.x, nh.y, nh.z, col.x);
+    g[4] = make_float4(col.y, col.z, 0.f, 0.f);
+}
+
+cudaError_t launch_tri_prep(Ctx* c, cudaStream_t s) {
+    if (c->T == 0) return cudaSuccess;
+    tri_prep_kernel<<<(c->T + 255) / 256, 256, 0, s>>>(c->raw.as<unsigned char>(), c->stride, c->T,
+                                                       c->geom.as<float4>());
+    c->launches++;
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Per (origin, triangle) constants.
+// ---------------------------------------------------------------------------
+struct TriG {
+    V3 v0, e1, e2, n;
+};
+__device__ __forceinline__ TriG load_geom(const float4* g) {
+    float4 a = g[0], b = g[1], c = g[2];
+    TriG t;
+    t.v0 = mk3(a.x, a.y, a.z);
+    t.e1 = mk3(a.w, b.x, b.y);
+    t.e2 = mk3(b.z, b.w, c.x);
+    t.n = mk3(c.y, c.z, c.w);
+    return t;
+}
+
+// Margin scale: coefficients are divided by M = 2^-18 * L1 where
+// L1 = |n|_1 + |b x e2|_1 + |e1 x b|_1, so that the margin is exactly
+// 1 * |dir|_inf.  Error budget in those units (u = 2^-24):
+//   reference's own dot products (5 roundings each)      3u*L1/M          = 0.047
+//   its u+v<=1 test on rounded quotients                 4u*L1/M          = 0.063
+//   primary rays: dir = fl(cameraRot*d) vs exact R*d     3u*L1/M          = 0.047
+//   our coefficients (rounded once) + FMA chain          4u*2^18          = 0.063
+// total < 0.25, i.e. the margin of 1 has >= 4x slack.
+__device__ void setup_origin_triangle(const float4* g, V3 org, bool primary, const DevFrame* f,
+                                      float4* out) {
+    TriG t = load_geom(g);
+    V3 b = xsub3(org, t.v0);       // raytracer.cpp:218
+    V3 be2 = xcross3(b, t.e2);     // :226
+    V3 e1b = xcross3(t.e1, b);     // :227
+    // :231 hand-written dot, left to right
+    float nb = xadd(xadd(xmul(t.n.x, b.x), xmul(t.n.y, b.y)), xmul(t.n.z, b.z));
+    out[0] = make_float4(be2.x, be2.y, be2.z, nb);
+    out[1] = make_float4(e1b.x, e1b.y, e1b.z, 0.f);
+
+    double s = (nb > 0.f) ? 1.0 : ((nb < 0.f) ? -1.0 : 0.0);
+    if (fabsf(nb) < 7.9e-31f) s = 0.0;  // 2^-100: t = nb/d0 could flush to +-0 (accepted by `t >= 0`)
+    double L1 = fabs((double)t.n.x) + fabs((double)t.n.y) + fabs((double)t.n.z) + fabs((double)be2.x) +
+                fabs((double)be2.y) + fabs((double)be2.z) + fabs((double)e1b.x) + fabs((double)e1b.y) +
+                fabs((double)e1b.z);
+    bool ok = (s != 0.0) && (L1 > 8.7e-19) && (L1 < 1.1e18);  // 2^-60 .. 2^60, also false for NaN/inf
+    float4 q[3];
+    if (ok) {
+        double invM = 262144.0 / L1;  // 1/M
+        double c[3][3] = {
+            {-s * be2.x * invM, -s * be2.y * invM, -s * be2.z * invM},
+            {-s * e1b.x * invM, -s * e1b.y * invM, -s * e1b.z * invM},
+            {-s * ((double)t.n.x - be2.x - e1b.x) * invM, -s * ((double)t.n.y - be2.y - e1b.y) * invM,
+             -s * ((double)t.n.z - be2.z - e1b.z) * invM}};
+        if (primary) {
+            // dir = col0*dx + col1*dy + col2*focal  (cameraRot*d, raytracer.cpp:579-580)
+            const float* R = f->R;
+            for (int k = 0; k < 3; ++k) {
+                double B = c[k][0] * R[0] + c[k][1] * R[1] + c[k][2] * R[2];
+                double C = c[k][0] * R[3] + c[k][1] * R[4] + c[k][2] * R[5];
+                double A = (c[k][0] * R[6] + c[k][1] * R[7] + c[k][2] * R[8]) * (double)f->focal +
+                           (double)f->primaryDmax;
+                q[k] = make_float4((float)B, (float)C, (float)A, 0.f);
+                ok = ok && isfinite(q[k].x) && isfinite(q[k].y) && isfinite(q[k].z);
+            }
+        } else {
+            for (int k = 0; k < 3; ++k) q[k] = make_float4((float)c[k][0], (float)c[k][1], (float)c[k][2], 0.f);
+        }
+    }
+    if (!ok) {  // always a candidate: the exact path decides
+        for (int k = 0; k < 3; ++k) q[k] = primary ? make_float4(0.f, 0.f, 1.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    out[2] = q[0];
+    out[3] = q[1];
+    out[4] = q[2];
+}
+
+// ---------------------------------------------------------------------------
+// The exact test: ClosestIntersection's loop body, raytracer.cpp:229-252.
+// nd = -dir.  Returns true when the reference accepts the hit; pos/dist valid then.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool exact_hit(const float4* g, const float4* xo, V3 start, V3 nd, V3& pos,
+                                          float& dist) {
+    TriG t = load_geom(g);
+    float4 q0 = xo[0], q1 = xo[1];
+    float d0 = xadd(xadd(xmul(t.n.x, nd.x), xmul(t.n.y, nd.y)), xmul(t.n.z, nd.z));    // e1e2d :232
+    float d1 = xadd(xadd(xmul(q0.x, nd.x), xmul(q0.y, nd.y)), xmul(q0.z, nd.z));       // be2d  :233
+    float d2 = xadd(xadd(xmul(q1.x, nd.x), xmul(q1.y, nd.y)), xmul(q1.z, nd.z));       // e1bd  :234
+    float tt = xdiv(q0.w, d0), u = xdiv(d1, d0), v = xdiv(d2, d0);                     // :237
+    if (!(xadd(u, v) <= 1.0f && u >= 0.0f && v >= 0.0f && tt >= 0.0f)) return false;   // :239
+    pos = xadd3(xadd3(t.v0, xscale3(t.e1, u)), xscale3(t.e2, v));                      // :241
+    V3 dv = xsub3(pos, start);                                                         // glm::distance(start,pos)
+    dist = xsqrt(xdot3(dv, dv));                                                       // :242
+    return true;
+}
+
+struct PixelState {  // == struct Intersection (+ the focalDistances slot), raytracer.cpp:91-96,249
+    V3 pos;
+    float dist;
+    int idx;
+    float focal;
+};
+
+template <bool STATS>
+struct Counters {
+    unsigned long long primary = 0, shadow = 0, exact = 0;
+};
+template <>
+struct Counters<false> {};
+
+// ---------------------------------------------------------------------------
+// The kernel.
+// ---------------------------------------------------------------------------
+constexpr int kTileW = 32, kTileH = 8, kThreads = 256;
+
+template <bool FILTER, bool STATS>
+__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const int T = a.T;
+    const DevFrame* __restrict__ f = a.frame;
+    const int nO = f->nOrigins;
+    float4* sG = reinterpret_cast<float4*>(smem_raw);            // T * kGeomQuads
+    float4* sX = sG + (size_t)T * kGeomQuads;                    // nO * T * kOriginQuads
+    float4* sOrg = sX + (size_t)nO * T * kOriginQuads;           // nO origins
+    float4* sPow = sOrg + nO;                                    // nLights light powers
+
+    // 1. triangles: HBM -> shared by one bulk async copy
+    const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, geomBytes);
+        bulk_g2s(sG, a.geom, geomBytes, &bar);
+    }
+    for (int i = threadIdx.x; i < nO; i += kThreads)
+        sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
+    for (int i = threadIdx.x; i < f->nLights; i += kThreads)
+        sPow[i] = make_float4(f->lightPower[i][0], f->lightPower[i][1], f->lightPower[i][2], 0.f);
+    mbar_wait(&bar, 0);
+    __syncthreads();
+
+    // 2. per (origin, triangle) constants
+    for (int it = threadIdx.x; it < nO * T; it += kThreads) {
+        int o = it / T, i = it - o * T;
+        float4 og = sOrg[o];
+        setup_origin_triangle(sG + (size_t)i * kGeomQuads, mk3(og.x, og.y, og.z), o == 0, f,
+                              sX + (size_t)it * kOriginQuads);
+    }
+    __syncthreads();
+
+    const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
+    float R[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = f->R[i];
+    const float focalLength = f->focal, dofFocal = f->dofFocal;
+    const V3 indirect = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
+    const int N = f->aaN, nLights = f->nLights, samples = f->samples;
+    const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
+    const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
+    const float invNN = (float)(N * N);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Counters<STATS> cnt;
+
+    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
+        const int x = tx * kTileW + (warp & 3) * 8 + (lane & 7);
+        const int y = a.y0 + ty * kTileH + (warp >> 2) * 4 + (lane >> 3);
+        if (x >= a.W || y >= a.y1) continue;
+
+        PixelState ps;  // Update()'s per-frame reset, raytracer.cpp:335-339 (+P5)
+        ps.pos = mk3(0.f, 0.f, 0.f);
+        ps.dist = FLT_MAX;
+        ps.idx = -1;
+        ps.focal = 0.f;
+        V3 avg = mk3(0.f, 0.f, 0.f);
+        float y1 = (N > 1) ? xsub((float)y, 0.5f) : (float)y;  // :564-567
+        for (int z = 0; z < N; ++z) {
+            float x1 = (N > 1) ? xsub((float)x, 0.5f) : (float)x;  // :571-574
+            for (int z2 = 0; z2 < N; ++z2) {
+                // ---- primary ray :579-580
+                const float dx = xsub(x1, halfW), dy = xsub(y1, halfH);
+                const V3 dir = xmat_vec(R, mk3(dx, dy, focalLength));
+                const V3 nd = neg3(dir);  // :229
+                bool any = false;
+                if constexpr (STATS) cnt.primary++;
+                const float4* xo = sX;  // origin 0
+                for (int i = 0; i < T; ++i) {
+                    bool cand = true;
+                    if (FILTER) {
+                        float4 c1 = xo[i * kOriginQuads + 2], c2 = xo[i * kOriginQuads + 3],
+                               c3 = xo[i * kOriginQuads + 4];
+                        float E1 = fmaf(c1.x, dx, fmaf(c1.y, dy, c1.z));
+                        float E2 = fmaf(c2.x, dx, fmaf(c2.y, dy, c2.z));
+                        float E3 = fmaf(c3.x, dx, fmaf(c3.y, dy, c3.z));
+                        cand = (__float_as_int(E1) | __float_as_int(E2) | __float_as_int(E3)) >= 0;
+                    }
+                    if (cand) {
+                        if constexpr (STATS) cnt.exact++;
+                        V3 pos;
+                        float dist;
+                        if (exact_hit(sG + i * kGeomQuads, xo + i * kOriginQuads, cam, nd, pos, dist)) {
+                            if (ps.dist >= dist) {  // :243 ties -> later index
+                                ps.pos = pos;
+                                ps.dist = dist;
+                                ps.idx = i;
+                                ps.focal = xsub(dist, dofFocal);  // :249
+                            }
+                            any = true;  // :251
+                        }
+                    }
+                }
+                if (any) {
+                    // ---- DirectLight :265-327
+                    const float4 g3 = sG[ps.idx * kGeomQuads + 3], g4 = sG[ps.idx * kGeomQuads + 4];
+                    const V3 nDir = mk3(g3.x, g3.y, g3.z);
+                    const V3 colr = mk3(g3.w, g4.x, g4.y);
+                    V3 result = mk3(0.f, 0.f, 0.f), result2 = mk3(0.f, 0.f, 0.f);
+                    for (int k = 0; k < nLights; ++k) {
+                        const float4 pw = sPow[k];
+                        const V3 P = mk3(pw.x, pw.y, pw.z);  // (color*intensity)/samples :282,296
+                        for (int s = 0; s < samples; ++s) {
+                            const int o = 1 + k * samples + s;
+                            const float4 og = sOrg[o];
+                            const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
+                            const V3 dv = xsub3(lpos, ps.pos);       // position - i.position
+                            const float rr = xdot3(dv, dv);
+                            const float r = xsqrt(rr);               // :294
+                            const float A = sphere_area(r);          // :295
+                            const V3 rDir = xscale3(dv, xdiv(1.0f, r));  // :298 normalize
+                            const V3 B = xdivs3(P, A);               // :301
+                            V3 D = xscale3(B, std_max(xdot3(rDir, nDir), 0.0f));  // :304
+                            // ---- shadow ray from the light towards the surface :307-315
+                            // direction -rDir, so -dir == rDir; occluded iff any accepted hit is
+                            // closer than r*0.99f (== j.distance < r*0.99f, j the closest hit)
+                            const float thr = xmul(r, 0.99f);
+                            bool occluded = false;
+                            if constexpr (STATS) cnt.shadow++;
+                            const float4* xs = sX + (size_t)o * T * kOriginQuads;
+                            for (int i = 0; i < T; ++i) {
+                                bool cand = true;
+                                if (FILTER) {
+                                    float4 c1 = xs[i * kOriginQuads + 2], c2 = xs[i * kOriginQuads + 3],
+                                           c3 = xs[i * kOriginQuads + 4];
+                                    // forms are in terms of dir = -rDir
+                                    float E1 = fmaf(c1.x, rDir.x, fmaf(c1.y, rDir.y, c1.z * rDir.z));
+                                    float E2 = fmaf(c2.x, rDir.x, fmaf(c2.y, rDir.y, c2.z * rDir.z));
+                                    float E3 = fmaf(c3.x, rDir.x, fmaf(c3.y, rDir.y, c3.z * rDir.z));
+                                    // E(dir) = -E(rDir); candidate unless some form < -|dir|_inf (<= 1)
+                                    cand = !(fmaxf(fmaxf(E1, E2), E3) > 1.0001f);
+                                }
+                                if (cand) {
+                                    if constexpr (STATS) cnt.exact++;
+                                    V3 pos;
+                                    float dist;
+                                    if (exact_hit(sG + i * kGeomQuads, xs + i * kOriginQuads, lpos, rDir, pos, dist)) {
+                                        if (dist < thr) {
+                                            occluded = true;
+                                            break;
+                                        }
+                                    }
+                                }
+                            }
+                            if (occluded) D = mk3(0.f, 0.f, 0.f);
+                            result = xadd3(result, D);      // :319
+                        }
+                        result2 = xadd3(result2, result);   // :322 (result is not reset per light)
+                    }
+                    const V3 color = xmul3(result2, colr);  // :325-326
+                    const V3 Tsum = xadd3(color, indirect); // :586
+                    avg = xadd3(avg, xmul3(colr, Tsum));    // :587-591
+                    x1 = xadd(x1, stepAA);                  // :593 -- only after a hit
+                }
+            }
+            y1 = xadd(y1, stepAA);  // :596
+        }
+        avg = xdivs3(avg, invNN);  // :599
+        const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;  // P2: row stride = width
+        if (a.colours) {
+            a.colours[3 * idx] = avg.x;
+            a.colours[3 * idx + 1] = avg.y;
+            a.colours[3 * idx + 2] = avg.z;
+        }
+        if (a.closest) {
+            b2r_intersection* c = a.closest + idx;
+            c->position[0] = ps.pos.x;
+            c->position[1] = ps.pos.y;
+            c->position[2] = ps.pos.z;
+            c->distance = ps.dist;
+            c->triangleIndex = ps.idx;
+        }
+        if (a.focal) a.focal[idx] = ps.focal;
+    }
+
+    if constexpr (STATS) {
+        unsigned long long v[3] = {cnt.primary, cnt.shadow, cnt.exact};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            unsigned long long s = v[k];
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0 && s) atomicAdd(a.stats + k, s);
+        }
+    }
+}
+
+static size_t rt_smem_bytes(int T, int nO, int nLights) {
+    return ((size_t)T * kGeomQuads + (size_t)nO * T * kOriginQuads + nO + nLights) * 16;
+}
+
+cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
+    const int nO = c->hostFrame.nOrigins;
+    const size_t smem = rt_smem_bytes(a.T, nO, c->hostFrame.nLights);
+    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;  // reported as B2R_E_UNSUPPORTED by the caller
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<true, true> : rt_trace_shade_kernel<true, false>)
+                            : (a.stats ? rt_trace_shade_kernel<false, true> : rt_trace_shade_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int perSM = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (perSM < 1) perSM = 1;
+    int grid = c->smCount * perSM;
+    if (grid > a.numTiles) grid = a.numTiles;
+    if (grid < 1) return cudaSuccess;
+    kern<<<grid, kThreads, smem, s>>>(a);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace b2r

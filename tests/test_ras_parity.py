@@ -1,0 +1,148 @@
+"""Rasteriser parity: CUDA path (through the C ABI) vs the CPU oracle.
+
+Criteria (north star): coverage and depth winner bit-exact, colour within 1e-4.  Depth values,
+focal distances and colours are in fact bit-exact here and asserted as such.
+"""
+import numpy as np
+import pytest
+
+from util import bits, random_soup, rot_y
+
+pytestmark = pytest.mark.gpu
+COLOUR_TOL = 1e-4
+
+
+def check(got, want):
+    assert np.array_equal(got["winner"], want["winner"]), int((got["winner"] != want["winner"]).sum())
+    assert np.array_equal(bits(got["depthBuffer"]), bits(want["depthBuffer"]))
+    assert np.abs(got["pixelColours"] - want["pixelColours"]).max() <= COLOUR_TOL
+    assert np.array_equal(bits(got["pixelColours"]), bits(want["pixelColours"]))
+    assert np.array_equal(bits(got["focalDistances"]), bits(want["focalDistances"]))
+
+
+def draw_both(pkg, oracle, tris, fp, w, h, cull=True):
+    ctx = pkg.Context(w, h)
+    ctx.enable_stats(True)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    if cull:
+        culled = ctx.ras_cull()
+        assert np.array_equal(culled, oracle.ras_cull(tris, fp, w, h))
+    else:
+        culled = np.zeros(len(tris), np.uint8)
+        ctx.set_culled(culled)
+    got = ctx.ras_draw()
+    st = ctx.stats()
+    ctx.close()
+    want = oracle.ras_draw(tris, culled, fp, w, h)
+    assert st["ras_triangles"] == want["triangles"] and st["ras_rows"] == want["rows"], (st, want["rows"])
+    assert st["ras_depth_tests"] == want["depth_tests"], (st, want["depth_tests"])
+    return got, want, culled
+
+
+def test_config2_cornell_500(pkg, oracle):
+    """BASELINE config 2: Cornell box 500x500, per-pixel illumination, 1/z depth buffer."""
+    w = h = 500
+    tris = pkg.cornell_box()
+    fp = pkg.default_frame_params(1, w, h)
+    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h)
+    check(got, want)
+    # known answers of the reference itself
+    assert "".join(map(str, culled)) == "000000000000001111000011110011"
+    assert int((got["winner"] >= 0).sum()) == 249498
+    assert want["depth_tests"] == 291070
+
+
+@pytest.mark.parametrize("w,h", [(96, 64), (64, 96), (160, 120), (33, 17)])
+def test_small_screens(pkg, oracle, w, h):
+    tris = pkg.cornell_box()
+    fp = pkg.default_frame_params(1, w, h)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h)
+    check(got, want)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_scenes(pkg, oracle, seed):
+    """Random soups in front of a rotated camera: off-screen spans, exact-zinv ties, several lights, no culling."""
+    rng = np.random.default_rng(seed)
+    w, h = 128, 96
+    tris = random_soup(rng, 60, spread=1.2, size=0.9)
+    tris[:, [2, 5, 8]] += 1.0  # keep every vertex in front of the camera
+    if seed == 4:  # duplicate triangles: exact depth ties must go to the lower index
+        tris[30:] = tris[:30]
+        tris[30:, 12:15] = rng.uniform(0.1, 0.9, (30, 3)).astype(np.float32)
+    fp = pkg.default_frame_params(1, w, h)
+    fp.set_camera([0.1, -0.05, -3.0], rot_y(rng.uniform(-0.2, 0.2), 1.01), float(h))
+    lights = np.concatenate([rng.uniform(-1, 1, (2, 3)), rng.uniform(0.2, 1, (2, 3)), rng.uniform(2, 20, (2, 1))], 1)
+    fp.set_lights(lights.astype(np.float32))
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, cull=(seed % 2 == 0))
+    check(got, want)
+    if seed == 4:
+        assert (got["winner"] < 30).all()
+
+
+def test_tessellated_cornell(pkg, oracle):
+    """BASELINE config 4 shape at reduced size: k=24 tessellation (17,280 triangles) at 640x360."""
+    w, h = 640, 360
+    tris = pkg.tessellate(pkg.cornell_box(), 24)
+    fp = pkg.default_frame_params(1, w, h)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h)
+    check(got, want)
+
+
+def test_config4_full_size(pkg, oracle):
+    """BASELINE config 4 at full size: 183x183 tessellation = 1,004,670 triangles at 3840x2160."""
+    w, h = 3840, 2160
+    tris = pkg.tessellate(pkg.cornell_box(), 183)
+    assert len(tris) == 1004670
+    fp = pkg.default_frame_params(1, w, h)
+    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h)
+    check(got, want)
+
+
+def test_row_bands_equal_full_frame(pkg, oracle):
+    w, h = 160, 120
+    tris = pkg.tessellate(pkg.cornell_box(), 6)
+    fp = pkg.default_frame_params(1, w, h)
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    ctx.ras_cull()
+    full = ctx.ras_draw()
+    merged = {k: np.zeros_like(v) for k, v in full.items()}
+    merged["winner"][:] = -1
+    for y0, y1 in ((0, 41), (41, 41), (41, 120)):
+        part = ctx.ras_draw(y0, y1)
+        for k in merged:
+            merged[k][y0:y1] = part[k][y0:y1]
+    for k in full:
+        assert np.array_equal(full[k].view(np.uint8), merged[k].view(np.uint8)), k
+    ctx.close()
+
+
+def test_empty_and_all_culled(pkg, oracle):
+    w, h = 64, 48
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(np.zeros((0, 15), np.float32))
+    ctx.set_frame(pkg.default_frame_params(1, w, h))
+    got = ctx.ras_draw()
+    assert (got["winner"] == -1).all() and not got["depthBuffer"].any() and not got["pixelColours"].any()
+    tris = pkg.cornell_box()
+    ctx.set_triangles(tris)
+    ctx.set_culled(np.ones(len(tris), np.uint8))
+    got = ctx.ras_draw()
+    assert (got["winner"] == -1).all()
+    ctx.close()
+
+
+def test_vertex_behind_camera_is_refused(pkg):
+    """A vertex on the camera plane projects to +-inf: the reference would walk ~2^31 rows; we return an error."""
+    w, h = 64, 48
+    tris = pkg.cornell_box()[:1].copy()
+    tris[0, 2] = -3.0  # v0.z == cameraPos.z
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(tris)
+    ctx.set_frame(pkg.default_frame_params(1, w, h))
+    with pytest.raises(pkg.B2RError):
+        ctx.ras_draw()
+    ctx.close()
