@@ -1,0 +1,408 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the render hot paths (one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json config 3, named in config.workload): the Cornell box raytraced at
+3840x2160 with AA 4x4 = 16 sub-samples per pixel and one hard-shadow ray per hit sample.
+A "step" is one Draw() (trace + shade + resolve to the 32-bit surface) of one frame.
+metric = Mrays/s, a ray being one ClosestIntersection call (primary + shadow rays actually cast,
+counted by the kernel's own counters in an untimed pass).
+
+  value         device-resident: inputs already in HBM, CUDA events around each step on the
+                launching stream, L2 flushed between steps, max over ranks.
+  e2e           the same metric through the host-buffer C ABI call a reference user makes
+                (b2r_set_frame + b2r_rt_frame): frame constants H2D from pinned memory and the
+                32-bit surface D2H to pinned memory inside the timed region.
+  roofline      rt_trace_shade kernel alone: algorithmic flops / mean launch time,
+                against the FP32 FFMA peak measured in this run (MEASURED_PEAKS.json has no FP32 entry).
+  cpu_baseline  the reference's own raytracer.cpp (oracle/_ref, compiled from /root/reference)
+                timed on this host's cores on a bounded row sample of the same workload.
+  extra         the other BASELINE configs (rasteriser 500^2 and 4K/1M triangles, raytracer 500^2).
+
+N > 1: one process per GPU, frames partitioned across ranks (no data-path collective, weak
+scaling); extra.band_split reports the single-frame row-band split with an NCCL all-gather.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W4K, H4K = 3840, 2160
+WORKLOAD = "raytracer Cornell box (30 tris) 3840x2160, AA 4x4 = 16 samples/pixel, primary + shadow ray"
+FLOP_PER_TEST, FLOP_PER_HIT, FLOP_PER_SHADE = 19, 21, 70
+
+
+def algorithmic_flops(primary, shadow, ntris, lights_x_samples):
+    """19 per ray/triangle test, 21 per accepted hit (one per hitting ray), 70 per shaded sample."""
+    shaded = shadow // max(lights_x_samples, 1)
+    return FLOP_PER_TEST * ntris * (primary + shadow) + FLOP_PER_HIT * (shaded + shadow) + FLOP_PER_SHADE * shaded
+
+
+def rt4k_params(pkg):
+    fp = pkg.default_frame_params(0, W4K, H4K)
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    return fp
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the only place that may execute oracle/)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(pkg, row_step, steps, warmup):
+    """Times the reference CPU implementation on rows 0, row_step, 2*row_step, ... of the workload."""
+    from oracle import refbind, portbind
+    cores = os.cpu_count() or 1
+    fp = rt4k_params(pkg)
+    tris = pkg.cornell_box()
+    rows = len(range(0, H4K, row_step))
+    # rays of the sample, from the port's counters (identical arithmetic, untimed)
+    cnt = portbind.rt_draw(tris, fp, W4K, H4K, 0, H4K, threads=cores, ystep=row_step)
+    rays = cnt["primary_rays"] + cnt["shadow_rays"]
+    if refbind.available("rt", W4K, H4K):
+        kind = "reference"
+        rt = refbind.RefRaytracer(W4K, H4K)
+        rt.load_test_model()
+        rt.set_lights(fp.lights_array())
+        rt.set_camera(fp.cameraPos[:], fp.cameraRot[:], fp.focalLength)
+        rt.set_flags(aa=True, aa_samples=4, threads=cores)
+        rt.set_rows(0, H4K, row_step)
+        run = rt.time_draw
+    else:
+        kind = "port"
+        def run():
+            t0 = time.perf_counter()
+            portbind.rt_draw(tris, fp, W4K, H4K, 0, H4K, threads=cores, ystep=row_step)
+            return time.perf_counter() - t0
+    for _ in range(warmup):
+        run()
+    secs = [run() for _ in range(steps)]
+    mean = sum(secs) / len(secs)
+    return dict(value=rays / mean / 1e6, unit="Mrays/s", cores=cores, kind=kind,
+                sample=f"{rows} of {H4K} rows (every {row_step}th) of the 4K AA4x4 frame, {rays} rays per step, "
+                       f"{steps} steps, OpenMP on all {cores} host threads",
+                ms_per_step=mean * 1e3, rays_per_step=rays)
+
+
+def run_reference_arm(args, pkg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_sample(pkg, row_step=34, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": base["sample"]},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()  # the exact PID we started
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smmax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu_arm(args, pkg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    stream = torch.cuda.Stream(device=dev)
+    tris = pkg.cornell_box()
+    fp = rt4k_params(pkg)
+    ctx = pkg.Context(W4K, H4K, device=local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    npx = W4K * H4K
+    d_col = torch.empty((H4K, W4K, 3), dtype=torch.float32, device=dev)
+    d_surf = torch.empty((H4K, W4K), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def frame_device():
+        ctx.rt_draw_device_async(0, H4K, d_col.data_ptr())
+        ctx.resolve_surface_device_async(0, H4K, d_col.data_ptr(), 0, d_surf.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # untimed: ray counts of one frame from the kernel's counters
+    ctx.enable_stats(True)
+    frame_device()
+    st = ctx.stats()
+    ctx.enable_stats(False)
+    rays = st["primary_rays"] + st["shadow_rays"]
+    flops = algorithmic_flops(st["primary_rays"], st["shadow_rays"], len(tris), fp.numLights * 1)
+
+    def timed_loop(fn, steps, warmup, do_flush=True):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                fn()
+            barrier()
+            evs = []
+            for _ in range(steps):
+                if do_flush:
+                    flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                evs.append((e0, e1))
+            barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)  # ms over all steps, device time
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    total_ms = timed_loop(frame_device, args.steps, args.warmup)
+    launches = ctx.launch_count() - launches0 - 2 * args.warmup
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * rays * args.steps / (total_ms * 1e-3) / 1e6  # whole-job Mrays/s
+
+    # roofline: the trace kernel alone
+    kern_ms = timed_loop(lambda: ctx.rt_draw_device_async(0, H4K, d_col.data_ptr()), args.steps, 1) / args.steps
+    peak_tf, _ = ctx.measure_fp32_peak()
+    achieved_tf = flops / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "rt_trace_shade_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # e2e: host-buffer C ABI, pinned host memory, H2D of the frame constants + D2H of the surface every step
+    surf_host = torch.empty((H4K, W4K), dtype=torch.int32).pin_memory()
+    surf_np = surf_host.numpy().view(np.uint32)
+    def frame_e2e():
+        ctx.set_frame(fp)
+        ctx.rt_frame(surf_np)
+    for _ in range(max(args.warmup, 1)):
+        frame_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        frame_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * rays * args.steps / e2e_s / 1e6
+    h2d_bytes = 1728 + 16 * (1 + fp.numLights)  # DevFrame up to and including the used ray origins (b2r_set_frame)
+    d2h_bytes = npx * 4
+
+    extra = {"frames_per_s": world * args.steps / (total_ms * 1e-3), "rays_per_frame": rays,
+             "algorithmic_gflop_per_frame": flops / 1e9, "e2e_frames_per_s": world * args.steps / e2e_s}
+
+    # single-frame row-band split + NCCL all-gather of the surface bands (strong scaling, N > 1 only)
+    if world > 1 and H4K % world == 0:
+        band = H4K // world
+        y0, y1 = rank * band, (rank + 1) * band
+        def frame_band():
+            ctx.rt_draw_device_async(y0, y1, d_col.data_ptr())
+            ctx.resolve_surface_device_async(y0, y1, d_col.data_ptr(), 0, d_surf.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(d_surf.view(-1), d_surf.view(-1)[y0 * W4K:y1 * W4K])
+        bms = timed_loop(frame_band, args.steps, args.warmup)
+        t = torch.tensor([bms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        bms = float(t.item()) / args.steps
+        extra["band_split"] = {"ms_per_frame": bms, "value": rays / (bms * 1e-3) / 1e6, "unit": "Mrays/s",
+                               "scaling": "strong", "collective": "nccl all_gather of 32-bit surface bands"}
+
+    if rank == 0:
+        extra.update(other_configs(pkg, torch, dev, stream, flush, local))
+        cpu = cpu_reference_sample(pkg, row_step=34, steps=1, warmup=0) if world == 1 and not args.no_cpu else None
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": f"frames x{world}",
+                       "l2": "flushed between steps (256 MB fill)", "outputs": "pixelColours + 32-bit surface in HBM"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "call": "b2r_set_frame + b2r_rt_frame (pinned host surface)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                         "kernel": "rt_trace_shade_kernel", "kernel_ms": kern_ms,
+                         "peak_source": "FFMA microbenchmark measured in this run (b2r_measure_fp32_peak); "
+                                        "MEASURED_PEAKS.json has no FP32 entry"},
+            "clocks": clocks,
+            "extra": extra,
+        }
+        if cpu:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def other_configs(pkg, torch, dev, stream, flush, local):
+    """The remaining BASELINE configs, device-timed (reported under extra, not the headline)."""
+    out = {}
+    tris = pkg.cornell_box()
+
+    def avg_ms(fn, n=10, warm=3):
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            tot = 0.0
+            for _ in range(n):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                torch.cuda.synchronize(dev)
+                tot += e0.elapsed_time(e1)
+        return tot / n
+
+    # config 1: raytracer 500x500
+    ctx = pkg.Context(500, 500, device=local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_triangles(tris)
+    ctx.set_frame(pkg.default_frame_params(0, 500, 500))
+    col = torch.empty((500, 500, 3), dtype=torch.float32, device=dev)
+    surf = torch.empty((500, 500), dtype=torch.int32, device=dev)
+    def f1():
+        ctx.rt_draw_device_async(0, 500, col.data_ptr())
+        ctx.resolve_surface_device_async(0, 500, col.data_ptr(), 0, surf.data_ptr())
+    ms = avg_ms(f1)
+    out["rt_500x500"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "Mrays_per_s": 500000 / ms / 1e3}
+    # config 2: rasteriser 500x500
+    ctx.set_frame(pkg.default_frame_params(1, 500, 500))
+    ctx.ras_cull()
+    dep = torch.empty((500, 500), dtype=torch.float32, device=dev)
+    def f2():
+        ctx.ras_draw_device_async(0, 500, dep.data_ptr(), col.data_ptr())
+        ctx.resolve_surface_device_async(0, 500, col.data_ptr(), 0, surf.data_ptr())
+    ms = avg_ms(f2)
+    out["ras_500x500"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms}
+    ctx.close()
+    # config 4: rasteriser 4K, 1,004,670 triangles
+    big = pkg.tessellate(tris, 183)
+    ctx = pkg.Context(W4K, H4K, device=local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_triangles(big)
+    ctx.set_frame(pkg.default_frame_params(1, W4K, H4K))
+    ctx.ras_cull()
+    dep = torch.empty((H4K, W4K), dtype=torch.float32, device=dev)
+    col = torch.empty((H4K, W4K, 3), dtype=torch.float32, device=dev)
+    ms = avg_ms(lambda: ctx.ras_draw_device_async(0, H4K, dep.data_ptr(), col.data_ptr()))
+    abytes = 64 * len(big) + 16 * W4K * H4K
+    peak = None
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    src = "MEASURED_PEAKS.json hbm_gbs" if peak else "fallback 6650 GB/s (B200_PROFILING.md)"
+    peak = peak or 6650.0
+    out["ras_4k_1m_tris"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "triangles": len(big),
+                             "roofline": {"bound": "hbm", "achieved": abytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                          "frac": abytes / ms / 1e6 / peak, "algorithmic_bytes": abytes,
+                                          "peak_source": src, "scope": "whole Draw() pipeline, all kernels"}}
+    ctx.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b2r" else args.warmup
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    if args.impl == "reference":
+        run_reference_arm(args, pkg)
+    else:
+        run_gpu_arm(args, pkg)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,7 +52,12 @@ def patch_common(src, n_stride_sites):
 
 
 def patch_rt(src):
-    return patch_common(src, 9)
+    src = patch_common(src, 9)
+    # P7 (timing only): let the harness render a strided subset of rows so the CPU baseline can be a
+    # bounded, representative sample of a 4K frame.  Defaults (0, SCREEN_HEIGHT, 1) = the reference loop.
+    src = _sub(src, r"for \(int y = 0; y < SCREEN_HEIGHT; y\+\+\)",
+               "for (int y = ref_y0; y < ref_y1; y += ref_ystep)", 1, "P7")
+    return src
 
 
 def patch_ras(src):

@@ -124,12 +124,13 @@ ORACLE_API void oracle_rt_direct_light(const b2r_intersection* hit, const float*
 }
 
 /* ---- Draw ------------------------------------------------------------------
- * Rows [y0,y1) of a W x H frame.  Output arrays are full-frame (may be NULL).
+ * Rows y0, y0+ystep, ... < y1 of a W x H frame (ystep > 1 only for bounded timing samples).
+ * Output arrays are full-frame (may be NULL).
  * counters (may be NULL): [0] primary rays, [1] shadow rays. */
 ORACLE_API int oracle_rt_draw(const float* tris15, int T, const b2r_frame_params* fp, int W, int H,
-                              int y0, int y1, float* pixelColours, b2r_intersection* closestOut,
+                              int y0, int y1, int ystep, float* pixelColours, b2r_intersection* closestOut,
                               float* focalDistances, int threads, unsigned long long* counters) {
-    if (!tris15 || !fp || W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1) return -1;
+    if (!tris15 || !fp || W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1 || ystep < 1) return -1;
     const int N = fp->aaEnabled ? fp->aaSamples : 1; /* :551-554 */
     omat3 R;
     memcpy(&R, fp->cameraRot, sizeof R);
@@ -140,7 +141,7 @@ ORACLE_API int oracle_rt_draw(const float* tris15, int T, const b2r_frame_params
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 4) num_threads(threads > 0 ? threads : 1) reduction(+ : nPrimary, nShadow)
 #endif
-    for (int y = y0; y < y1; ++y) {
+    for (int y = y0; y < y1; y += ystep) {
         float x1 = 0.0f, y1f = 0.0f;
         for (int x = 0; x < W; ++x) {
             oisect c; /* per-frame reset :335-339 (+P5) */

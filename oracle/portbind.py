@@ -41,7 +41,7 @@ def _t15(tris):
     return np.ascontiguousarray(tris, np.float32).reshape(-1, 15)
 
 
-def rt_draw(tris15, fp, w, h, y0=0, y1=None, threads=None):
+def rt_draw(tris15, fp, w, h, y0=0, y1=None, threads=None, ystep=1):
     """oracle_rt_draw: returns dict like the reference harness."""
     t = _t15(tris15)
     y1 = h if y1 is None else y1
@@ -52,7 +52,7 @@ def rt_draw(tris15, fp, w, h, y0=0, y1=None, threads=None):
     foc = np.zeros((h, w), np.float32)
     cnt = (C.c_ulonglong * 2)()
     threads = threads or (os.cpu_count() or 1)
-    rc = lib().oracle_rt_draw(_p(t), len(t), C.byref(fp), w, h, y0, y1, _p(col), _p(clo), _p(foc), threads, cnt)
+    rc = lib().oracle_rt_draw(_p(t), len(t), C.byref(fp), w, h, y0, y1, ystep, _p(col), _p(clo), _p(foc), threads, cnt)
     assert rc == 0, rc
     return dict(pixelColours=col, closest=clo, focalDistances=foc, primary_rays=int(cnt[0]),
                 shadow_rays=int(cnt[1]))

@@ -9,7 +9,8 @@
 // (raytracer.cpp:28-98) and to Update()/Draw() (raytracer.cpp:329,547).
 //
 // P5 (triangleIndex = -1 for never-hit pixels) and P6 (main renamed) are done
-// here, not by editing the reference.
+// here, not by editing the reference.  P7 (row sampling, timing only) replaces
+// the bounds of Draw()'s row loop (raytracer.cpp:558) by harness variables.
 //
 // Exported C symbols: ref_rt_*.  One shared object per compile-time screen
 // size (-DREF_W=.. -DREF_H=..), because the reference sizes its static arrays
@@ -19,6 +20,9 @@
 #include <cstring>
 #include <iostream>
 #include <streambuf>
+
+// P7 state (row sampling for bounded timing runs), referenced by the patched Draw() loop.
+static int ref_y0 = 0, ref_y1 = REF_H, ref_ystep = 1;
 
 #define main ref_reference_main  // P6
 #include REF_PATCHED_SOURCE
@@ -157,6 +161,13 @@ REF_API void ref_rt_set_flags(int aa, int aaSamples, int soft, int softSamples, 
     DOF_ENABLED = dof != 0;
     FOCAL_LENGTH = dofFocalLength;
     if (threads > 0) omp_set_num_threads(threads);
+}
+
+// P7: Draw() visits rows y0, y0+step, ... < y1 (default: every row).
+REF_API void ref_rt_set_rows(int y0, int y1, int step) {
+    ref_y0 = y0;
+    ref_y1 = y1;
+    ref_ystep = step > 0 ? step : 1;
 }
 
 REF_API void ref_rt_set_indirect(const float v[3]) { indirectLight = vec3(v[0], v[1], v[2]); }

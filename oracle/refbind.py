@@ -92,6 +92,10 @@ class RefRaytracer:
     def time_draw(self):
         return self.lib.ref_rt_draw(None, None, None, None)
 
+    def set_rows(self, y0=0, y1=None, step=1):
+        """P7: restrict Draw() to rows y0, y0+step, ... (timing samples only)."""
+        self.lib.ref_rt_set_rows(y0, self.h if y1 is None else y1, step)
+
     def closest_intersection(self, start, direction, closest=None, is_light=False):
         c = np.zeros((), INTERSECTION_DTYPE)
         if closest is None:

@@ -1,0 +1,34 @@
+"""Short fixed command for ncu captures: a few launches of the hot kernels (no timing printed is a bench value)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as g
+pkg = g.load_package()
+W, H = 3840, 2160
+which = sys.argv[1] if len(sys.argv) > 1 else "rt"
+dev = torch.device("cuda:0")
+tris = pkg.cornell_box()
+if which == "rt":
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    fp = pkg.default_frame_params(0, W, H)
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    ctx.set_frame(fp)
+    col = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    surf = torch.empty((H, W), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ctx.rt_draw_device_async(0, H, col.data_ptr())
+        ctx.resolve_surface_device_async(0, H, col.data_ptr(), 0, surf.data_ptr())
+    ctx.synchronize()
+else:
+    big = pkg.tessellate(tris, 183)
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(big)
+    ctx.set_frame(pkg.default_frame_params(1, W, H))
+    ctx.ras_cull()
+    dep = torch.empty((H, W), dtype=torch.float32, device=dev)
+    col = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ctx.ras_draw_device_async(0, H, dep.data_ptr(), col.data_ptr())
+    ctx.synchronize()
+print("profile_run ok", which)
