@@ -33,6 +33,8 @@
 // identical (tests/test_rt_parity.py checks this).
 #include <float.h>
 
+#include <type_traits>
+
 #include "b2r_internal.h"
 #include "exact.cuh"
 
@@ -120,7 +122,9 @@ __device__ __forceinline__ TriG load_geom(const float4* g) {
     t.n = mk3(c.y, c.z, c.w);
     return t;
 }
-
+// ---------------------------------------------------------------------------
+// Conservative filter forms for one (ray origin, triangle) pair: 9 floats.
+//
 // Margin scale: coefficients are divided by M = 2^-18 * L1 where
 // L1 = |n|_1 + |b x e2|_1 + |e1 x b|_1, so that the margin is exactly
 // 1 * |dir|_inf.  Error budget in those units (u = 2^-24):
@@ -129,52 +133,85 @@ __device__ __forceinline__ TriG load_geom(const float4* g) {
 //   primary rays: dir = fl(cameraRot*d) vs exact R*d     3u*L1/M          = 0.047
 //   our coefficients (rounded once) + FMA chain          4u*2^18          = 0.063
 // total < 0.25, i.e. the margin of 1 has >= 4x slack.
-__device__ void setup_origin_triangle(const float4* g, V3 org, bool primary, const DevFrame* f,
-                                      float4* out) {
-    TriG t = load_geom(g);
-    V3 b = xsub3(org, t.v0);       // raytracer.cpp:218
-    V3 be2 = xcross3(b, t.e2);     // :226
-    V3 e1b = xcross3(t.e1, b);     // :227
-    // :231 hand-written dot, left to right
-    float nb = xadd(xadd(xmul(t.n.x, b.x), xmul(t.n.y, b.y)), xmul(t.n.z, b.z));
-    out[0] = make_float4(be2.x, be2.y, be2.z, nb);
-    out[1] = make_float4(e1b.x, e1b.y, e1b.z, 0.f);
+//
+// Primary rays (origin = camera): form k is  E_k(dx,dy) = B*dx + C*dy + A  with the
+// camera rotation, the focal length and the margin (A += primaryDmax) folded in;
+// out = {B1,C1,A1, B2,C2,A2, B3,C3,A3}.
+// Shadow rays (origin = light sample, -dir = rDir, |rDir| <= 1):
+// G_k(rDir) = g.rDir + 1.0001; out = {g1.xyz, g2.xyz, g3.xyz}.
+// The pair is rejected iff some form is negative (sign bit), never otherwise.
+// ---------------------------------------------------------------------------
+constexpr float kShadowMargin = 1.0001f;
 
+__host__ __device__ inline void filter_forms(V3 n, V3 be2, V3 e1b, float nb, bool primary, const float* R,
+                                             float focal, float primaryDmax, float* out) {
     double s = (nb > 0.f) ? 1.0 : ((nb < 0.f) ? -1.0 : 0.0);
-    if (fabsf(nb) < 7.9e-31f) s = 0.0;  // 2^-100: t = nb/d0 could flush to +-0 (accepted by `t >= 0`)
-    double L1 = fabs((double)t.n.x) + fabs((double)t.n.y) + fabs((double)t.n.z) + fabs((double)be2.x) +
-                fabs((double)be2.y) + fabs((double)be2.z) + fabs((double)e1b.x) + fabs((double)e1b.y) +
-                fabs((double)e1b.z);
-    bool ok = (s != 0.0) && (L1 > 8.7e-19) && (L1 < 1.1e18);  // 2^-60 .. 2^60, also false for NaN/inf
-    float4 q[3];
+    if (fabsf(nb) < 7.9e-31f) s = 0.0;  // 2^-100: t = nb/d0 could flush to +-0, which `t >= 0` accepts
+    const double L1 = fabs((double)n.x) + fabs((double)n.y) + fabs((double)n.z) + fabs((double)be2.x) +
+                      fabs((double)be2.y) + fabs((double)be2.z) + fabs((double)e1b.x) + fabs((double)e1b.y) +
+                      fabs((double)e1b.z);
+    bool ok = (s != 0.0) && (L1 > 8.7e-19) && (L1 < 1.1e18);  // 2^-60 .. 2^60; false for NaN/inf
     if (ok) {
-        double invM = 262144.0 / L1;  // 1/M
-        double c[3][3] = {
+        const double invM = 262144.0 / L1;  // 1/M
+        // forms in terms of dir:  c_k . dir  with c_k = -s * vec_k / M  (d_k = vec_k . (-dir), raytracer.cpp:232-234)
+        const double c[3][3] = {
             {-s * be2.x * invM, -s * be2.y * invM, -s * be2.z * invM},
             {-s * e1b.x * invM, -s * e1b.y * invM, -s * e1b.z * invM},
-            {-s * ((double)t.n.x - be2.x - e1b.x) * invM, -s * ((double)t.n.y - be2.y - e1b.y) * invM,
-             -s * ((double)t.n.z - be2.z - e1b.z) * invM}};
-        if (primary) {
-            // dir = col0*dx + col1*dy + col2*focal  (cameraRot*d, raytracer.cpp:579-580)
-            const float* R = f->R;
-            for (int k = 0; k < 3; ++k) {
-                double B = c[k][0] * R[0] + c[k][1] * R[1] + c[k][2] * R[2];
-                double C = c[k][0] * R[3] + c[k][1] * R[4] + c[k][2] * R[5];
-                double A = (c[k][0] * R[6] + c[k][1] * R[7] + c[k][2] * R[8]) * (double)f->focal +
-                           (double)f->primaryDmax;
-                q[k] = make_float4((float)B, (float)C, (float)A, 0.f);
-                ok = ok && isfinite(q[k].x) && isfinite(q[k].y) && isfinite(q[k].z);
+            {-s * ((double)n.x - be2.x - e1b.x) * invM, -s * ((double)n.y - be2.y - e1b.y) * invM,
+             -s * ((double)n.z - be2.z - e1b.z) * invM}};
+        for (int k = 0; k < 3; ++k) {
+            if (primary) {
+                // dir = col0*dx + col1*dy + col2*focal  (cameraRot*d, raytracer.cpp:579-580)
+                out[3 * k] = (float)(c[k][0] * R[0] + c[k][1] * R[1] + c[k][2] * R[2]);
+                out[3 * k + 1] = (float)(c[k][0] * R[3] + c[k][1] * R[4] + c[k][2] * R[5]);
+                out[3 * k + 2] = (float)((c[k][0] * R[6] + c[k][1] * R[7] + c[k][2] * R[8]) * (double)focal +
+                                         (double)primaryDmax);
+            } else {
+                // in terms of rDir = -dir
+                out[3 * k] = (float)(-c[k][0]);
+                out[3 * k + 1] = (float)(-c[k][1]);
+                out[3 * k + 2] = (float)(-c[k][2]);
             }
-        } else {
-            for (int k = 0; k < 3; ++k) q[k] = make_float4((float)c[k][0], (float)c[k][1], (float)c[k][2], 0.f);
+            ok = ok && isfinite(out[3 * k]) && isfinite(out[3 * k + 1]) && isfinite(out[3 * k + 2]);
         }
     }
-    if (!ok) {  // always a candidate: the exact path decides
-        for (int k = 0; k < 3; ++k) q[k] = primary ? make_float4(0.f, 0.f, 1.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    out[2] = q[0];
-    out[3] = q[1];
-    out[4] = q[2];
+    if (!ok)  // always a candidate: the exact path decides
+        for (int k = 0; k < 3; ++k) {
+            out[3 * k] = out[3 * k + 1] = 0.f;
+            out[3 * k + 2] = primary ? 1.f : 0.f;
+        }
+}
+
+// Everything in ClosestIntersection that depends only on `start` and the triangle
+// (raytracer.cpp:218,226-227,231), in reference operation order.
+struct OriginTri {
+    V3 be2, e1b;
+    float nb;
+};
+__host__ __device__ inline OriginTri origin_constants(V3 v0, V3 e1, V3 e2, V3 n, V3 org) {
+    OriginTri o;
+    const V3 b = xsub3(org, v0);   // :218
+    o.be2 = xcross3(b, e2);        // :226
+    o.e1b = xcross3(e1, b);        // :227
+    o.nb = xadd(xadd(xmul(n.x, b.x), xmul(n.y, b.y)), xmul(n.z, b.z));  // :231 hand-written dot, left to right
+    return o;
+}
+
+// Host side of the small-scene path: filter forms for every (origin, triangle) into the kernel-parameter block.
+void build_small_consts(const float* tris15, int T, const DevFrame& f, RtSmallConst* out) {
+    for (int o = 0; o < f.nOrigins; ++o)
+        for (int i = 0; i < kSmallTris; ++i) {
+            float* dst = out->f[o][i];
+            if (i >= T) {  // padding up to the unroll width; masked off in the kernel
+                for (int k = 0; k < 9; ++k) dst[k] = 0.f;
+                continue;
+            }
+            const float* t = tris15 + 15 * i;
+            const V3 v0 = mk3(t[0], t[1], t[2]), v1 = mk3(t[3], t[4], t[5]), v2 = mk3(t[6], t[7], t[8]);
+            const V3 e1 = xsub3(v1, v0), e2 = xsub3(v2, v0), n = xcross3(e1, e2);
+            const OriginTri c = origin_constants(v0, e1, e2, n, mk3(f.origin[o][0], f.origin[o][1], f.origin[o][2]));
+            filter_forms(n, c.be2, c.e1b, c.nb, o == 0, f.R, f.focal, f.primaryDmax, dst);
+        }
 }
 
 // ---------------------------------------------------------------------------
@@ -203,38 +240,108 @@ struct PixelState {  // == struct Intersection (+ the focalDistances slot), rayt
     float focal;
 };
 
-template <bool STATS>
 struct Counters {
     unsigned long long primary = 0, shadow = 0, exact = 0;
 };
-template <>
-struct Counters<false> {};
 
-// ---------------------------------------------------------------------------
-// The kernel.
-// ---------------------------------------------------------------------------
+// Shared-memory layout of one CTA.
+struct Smem {
+    const float4* G;  // T * kGeomQuads         scene-static triangle records
+    const float4* X;  // nO * T * 2             exact per-(origin,triangle) constants: (be2, nb), (e1b, 0)
+    const float4* F;  // nO * T * 3             filter forms (generic path only)
+    const float4* org;   // nO ray origins
+    const float4* power; // nLights light powers
+};
+
 constexpr int kTileW = 32, kTileH = 8, kThreads = 256;
 
-template <bool FILTER, bool STATS>
-__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch a) {
+// Candidate masks: bit (31 - j) set <=> triangle (base + j) must take the exact path.
+// The three forms are OR-ed as integers: any sign bit set = some form negative = certain reject.
+template <bool FILTER>
+__device__ __forceinline__ unsigned primary_candidates_small(const RtSmallConst& k, int T, float dx, float dy) {
+    const unsigned valid = T >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> T);  // entries >= T are padding
+    if (!FILTER) return valid;
+    unsigned rej = 0u;
+#pragma unroll
+    for (int i = 0; i < kSmallTris; ++i) {
+        const float* c = k.f[0][i];  // compile-time offsets: the coefficients are constant-bank operands of the FFMAs
+        const float E1 = fmaf(c[0], dx, fmaf(c[1], dy, c[2]));
+        const float E2 = fmaf(c[3], dx, fmaf(c[4], dy, c[5]));
+        const float E3 = fmaf(c[6], dx, fmaf(c[7], dy, c[8]));
+        rej = __funnelshift_l(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3), rej, 1);
+    }
+    return ~rej & valid;
+}
+
+template <bool FILTER, bool FIXED_ORIGIN>
+__device__ __forceinline__ unsigned shadow_candidates_small(const RtSmallConst& k, int T, int o, V3 r) {
+    const unsigned valid = T >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> T);
+    if (!FILTER) return valid;
+    unsigned rej = 0u;
+    const float(*f)[9] = FIXED_ORIGIN ? k.f[1] : k.f[o];
+#pragma unroll
+    for (int i = 0; i < kSmallTris; ++i) {
+        const float* c = f[i];
+        const float G1 = fmaf(c[0], r.x, fmaf(c[1], r.y, fmaf(c[2], r.z, kShadowMargin)));
+        const float G2 = fmaf(c[3], r.x, fmaf(c[4], r.y, fmaf(c[5], r.z, kShadowMargin)));
+        const float G3 = fmaf(c[6], r.x, fmaf(c[7], r.y, fmaf(c[8], r.z, kShadowMargin)));
+        rej = __funnelshift_l(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3), rej, 1);
+    }
+    return ~rej & valid;
+}
+
+// Generic path: forms in shared memory, a chunk of n <= 32 triangles starting at F (3 float4 per triangle).
+template <bool FILTER, bool PRIMARY>
+__device__ __forceinline__ unsigned candidates_smem(const float4* __restrict__ F, int n, float a, float b, float c3) {
+    const unsigned valid = n >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> n);
+    if (!FILTER) return valid;
+    unsigned rej = 0u;
+    for (int i = 0; i < n; ++i, F += 3) {
+        const float4 c1 = F[0], c2 = F[1], c3q = F[2];
+        float E1, E2, E3;
+        if (PRIMARY) {
+            E1 = fmaf(c1.x, a, fmaf(c1.y, b, c1.z));
+            E2 = fmaf(c2.x, a, fmaf(c2.y, b, c2.z));
+            E3 = fmaf(c3q.x, a, fmaf(c3q.y, b, c3q.z));
+        } else {
+            E1 = fmaf(c1.x, a, fmaf(c1.y, b, fmaf(c1.z, c3, kShadowMargin)));
+            E2 = fmaf(c2.x, a, fmaf(c2.y, b, fmaf(c2.z, c3, kShadowMargin)));
+            E3 = fmaf(c3q.x, a, fmaf(c3q.y, b, fmaf(c3q.z, c3, kShadowMargin)));
+        }
+        rej = __funnelshift_l(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3), rej, 1);
+    }
+    return ~(rej << (32 - n)) & valid;
+}
+
+// ---------------------------------------------------------------------------
+// The kernel.  SMALL: T <= 32 and few origins, filter forms in the parameter bank.
+// HARD1: exactly one light and one shadow sample (the reference's default), origin index fixed.
+// ---------------------------------------------------------------------------
+template <bool SMALL>
+using FilterArg = std::conditional_t<SMALL, RtSmallConst, int>;
+
+template <bool SMALL, bool HARD1, bool FILTER, bool STATS>
+__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a,
+                                                                  const __grid_constant__ FilterArg<SMALL> fa) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
     const DevFrame* __restrict__ f = a.frame;
     const int nO = f->nOrigins;
-    float4* sG = reinterpret_cast<float4*>(smem_raw);            // T * kGeomQuads
-    float4* sX = sG + (size_t)T * kGeomQuads;                    // nO * T * kOriginQuads
-    float4* sOrg = sX + (size_t)nO * T * kOriginQuads;           // nO origins
-    float4* sPow = sOrg + nO;                                    // nLights light powers
+    float4* sG = reinterpret_cast<float4*>(smem_raw);        // T * kGeomQuads
+    float4* sX = sG + (size_t)T * kGeomQuads;                // nO * T * 2
+    float4* sOrg = sX + (size_t)nO * T * 2;                  // nO
+    float4* sPow = sOrg + nO;                                // nLights
+    float4* sF = sPow + f->nLights;                          // nO * T * 3 (generic path only)
 
-    // 1. triangles: HBM -> shared by one bulk async copy
+    // 1. triangles: HBM -> shared memory by one bulk async copy (TMA), completion on an mbarrier
     const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && geomBytes) {
         mbar_expect_tx(&bar, geomBytes);
         bulk_g2s(sG, a.geom, geomBytes, &bar);
     }
@@ -242,15 +349,24 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
         sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
     for (int i = threadIdx.x; i < f->nLights; i += kThreads)
         sPow[i] = make_float4(f->lightPower[i][0], f->lightPower[i][1], f->lightPower[i][2], 0.f);
-    mbar_wait(&bar, 0);
+    if (geomBytes) mbar_wait(&bar, 0);
     __syncthreads();
 
-    // 2. per (origin, triangle) constants
+    // 2. per (origin, triangle) constants, once per CTA
     for (int it = threadIdx.x; it < nO * T; it += kThreads) {
-        int o = it / T, i = it - o * T;
-        float4 og = sOrg[o];
-        setup_origin_triangle(sG + (size_t)i * kGeomQuads, mk3(og.x, og.y, og.z), o == 0, f,
-                              sX + (size_t)it * kOriginQuads);
+        const int o = it / T, i = it - o * T;
+        const TriG t = load_geom(sG + (size_t)i * kGeomQuads);
+        const float4 og = sOrg[o];
+        const OriginTri c = origin_constants(t.v0, t.e1, t.e2, t.n, mk3(og.x, og.y, og.z));
+        sX[2 * it] = make_float4(c.be2.x, c.be2.y, c.be2.z, c.nb);
+        sX[2 * it + 1] = make_float4(c.e1b.x, c.e1b.y, c.e1b.z, 0.f);
+        if (!SMALL && FILTER) {
+            float q[9];
+            filter_forms(t.n, c.be2, c.e1b, c.nb, o == 0, f->R, f->focal, f->primaryDmax, q);
+            sF[3 * it] = make_float4(q[0], q[1], q[2], 0.f);
+            sF[3 * it + 1] = make_float4(q[3], q[4], q[5], 0.f);
+            sF[3 * it + 2] = make_float4(q[6], q[7], q[8], 0.f);
+        }
     }
     __syncthreads();
 
@@ -260,13 +376,14 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
     for (int i = 0; i < 9; ++i) R[i] = f->R[i];
     const float focalLength = f->focal, dofFocal = f->dofFocal;
     const V3 indirect = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
-    const int N = f->aaN, nLights = f->nLights, samples = f->samples;
+    const int N = f->aaN;
+    const int nLights = HARD1 ? 1 : f->nLights, samples = HARD1 ? 1 : f->samples;
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
     const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
     const float invNN = (float)(N * N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Counters<STATS> cnt;
+    Counters cnt;
 
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
@@ -290,22 +407,18 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
                 const V3 nd = neg3(dir);  // :229
                 bool any = false;
                 if constexpr (STATS) cnt.primary++;
-                const float4* xo = sX;  // origin 0
-                for (int i = 0; i < T; ++i) {
-                    bool cand = true;
-                    if (FILTER) {
-                        float4 c1 = xo[i * kOriginQuads + 2], c2 = xo[i * kOriginQuads + 3],
-                               c3 = xo[i * kOriginQuads + 4];
-                        float E1 = fmaf(c1.x, dx, fmaf(c1.y, dy, c1.z));
-                        float E2 = fmaf(c2.x, dx, fmaf(c2.y, dy, c2.z));
-                        float E3 = fmaf(c3.x, dx, fmaf(c3.y, dy, c3.z));
-                        cand = (__float_as_int(E1) | __float_as_int(E2) | __float_as_int(E3)) >= 0;
-                    }
-                    if (cand) {
+                for (int base = 0; base < T; base += 32) {
+                    unsigned cand;
+                    if constexpr (SMALL) cand = primary_candidates_small<FILTER>(fa, T, dx, dy);
+                    else cand = candidates_smem<FILTER, true>(sF + 3 * base, min(32, T - base), dx, dy, 0.f);
+                    while (cand) {  // ascending triangle index = descending bit
+                        const int j = __clz(cand);
+                        cand &= ~(0x80000000u >> j);
+                        const int i = base + j;
                         if constexpr (STATS) cnt.exact++;
                         V3 pos;
                         float dist;
-                        if (exact_hit(sG + i * kGeomQuads, xo + i * kOriginQuads, cam, nd, pos, dist)) {
+                        if (exact_hit(sG + i * kGeomQuads, sX + 2 * i, cam, nd, pos, dist)) {
                             if (ps.dist >= dist) {  // :243 ties -> later index
                                 ps.pos = pos;
                                 ps.dist = dist;
@@ -326,7 +439,7 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
                         const float4 pw = sPow[k];
                         const V3 P = mk3(pw.x, pw.y, pw.z);  // (color*intensity)/samples :282,296
                         for (int s = 0; s < samples; ++s) {
-                            const int o = 1 + k * samples + s;
+                            const int o = HARD1 ? 1 : 1 + k * samples + s;
                             const float4 og = sOrg[o];
                             const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
                             const V3 dv = xsub3(lpos, ps.pos);       // position - i.position
@@ -342,28 +455,23 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
                             const float thr = xmul(r, 0.99f);
                             bool occluded = false;
                             if constexpr (STATS) cnt.shadow++;
-                            const float4* xs = sX + (size_t)o * T * kOriginQuads;
-                            for (int i = 0; i < T; ++i) {
-                                bool cand = true;
-                                if (FILTER) {
-                                    float4 c1 = xs[i * kOriginQuads + 2], c2 = xs[i * kOriginQuads + 3],
-                                           c3 = xs[i * kOriginQuads + 4];
-                                    // forms are in terms of dir = -rDir
-                                    float E1 = fmaf(c1.x, rDir.x, fmaf(c1.y, rDir.y, c1.z * rDir.z));
-                                    float E2 = fmaf(c2.x, rDir.x, fmaf(c2.y, rDir.y, c2.z * rDir.z));
-                                    float E3 = fmaf(c3.x, rDir.x, fmaf(c3.y, rDir.y, c3.z * rDir.z));
-                                    // E(dir) = -E(rDir); candidate unless some form < -|dir|_inf (<= 1)
-                                    cand = !(fmaxf(fmaxf(E1, E2), E3) > 1.0001f);
-                                }
-                                if (cand) {
+                            const float4* xs = sX + (size_t)2 * o * T;
+                            for (int base = 0; base < T && !occluded; base += 32) {
+                                unsigned cand;
+                                if constexpr (SMALL) cand = shadow_candidates_small<FILTER, HARD1>(fa, T, o, rDir);
+                                else
+                                    cand = candidates_smem<FILTER, false>(sF + 3 * ((size_t)o * T + base),
+                                                                          min(32, T - base), rDir.x, rDir.y, rDir.z);
+                                while (cand) {
+                                    const int j = __clz(cand);
+                                    cand &= ~(0x80000000u >> j);
+                                    const int i = base + j;
                                     if constexpr (STATS) cnt.exact++;
                                     V3 pos;
                                     float dist;
-                                    if (exact_hit(sG + i * kGeomQuads, xs + i * kOriginQuads, lpos, rDir, pos, dist)) {
-                                        if (dist < thr) {
-                                            occluded = true;
-                                            break;
-                                        }
+                                    if (exact_hit(sG + i * kGeomQuads, xs + 2 * i, lpos, rDir, pos, dist) && dist < thr) {
+                                        occluded = true;
+                                        break;
                                     }
                                 }
                             }
@@ -409,16 +517,14 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const RtLaunch
     }
 }
 
-static size_t rt_smem_bytes(int T, int nO, int nLights) {
-    return ((size_t)T * kGeomQuads + (size_t)nO * T * kOriginQuads + nO + nLights) * 16;
+static size_t rt_smem_bytes(int T, int nO, int nLights, bool withForms) {
+    return ((size_t)T * kGeomQuads + (size_t)nO * T * (withForms ? 5 : 2) + nO + nLights) * 16;
 }
 
-cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
-    const int nO = c->hostFrame.nOrigins;
-    const size_t smem = rt_smem_bytes(a.T, nO, c->hostFrame.nLights);
-    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;  // reported as B2R_E_UNSUPPORTED by the caller
-    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<true, true> : rt_trace_shade_kernel<true, false>)
-                            : (a.stats ? rt_trace_shade_kernel<false, true> : rt_trace_shade_kernel<false, false>);
+template <bool SMALL, bool HARD1>
+static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, const FilterArg<SMALL>& fa, size_t smem, cudaStream_t s) {
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<SMALL, HARD1, true, true> : rt_trace_shade_kernel<SMALL, HARD1, true, false>)
+                            : (a.stats ? rt_trace_shade_kernel<SMALL, HARD1, false, true> : rt_trace_shade_kernel<SMALL, HARD1, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSM = 1;
@@ -428,9 +534,29 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
     int grid = c->smCount * perSM;
     if (grid > a.numTiles) grid = a.numTiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<grid, kThreads, smem, s>>>(a);
+    kern<<<grid, kThreads, smem, s>>>(a, fa);
     c->launches++;
     return cudaGetLastError();
+}
+
+// Variant selection (B2R_OPT_RT_VARIANT): 0 = automatic (small-scene path when it applies), 1 = force generic.
+cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
+    const DevFrame& f = c->hostFrame;
+    const bool small = c->optRtVariant != 1 && a.T <= kSmallTris && f.nOrigins <= kSmallMaxOrigins &&
+                       (int)c->hostTris.size() == 15 * a.T;
+    const bool hard1 = f.nLights == 1 && f.samples == 1;
+    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, !small);
+    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;  // reported as B2R_E_UNSUPPORTED by the caller
+    if (small) {
+        if (c->smallDirty) {
+            build_small_consts(c->hostTris.data(), a.T, f, &c->smallConsts);
+            c->smallDirty = false;
+        }
+        return hard1 ? launch_variant<true, true>(c, a, c->smallConsts, smem, s)
+                     : launch_variant<true, false>(c, a, c->smallConsts, smem, s);
+    }
+    const int none = 0;
+    return hard1 ? launch_variant<false, true>(c, a, none, smem, s) : launch_variant<false, false>(c, a, none, smem, s);
 }
 
 }  // namespace b2r

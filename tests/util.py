@@ -50,3 +50,33 @@ def rt_compare(got, want, tol=1e-4):
                 colours_bit_equal=bool(np.array_equal(bits(got["pixelColours"]), bits(want["pixelColours"]))),
                 closest_bit_equal=bool(np.array_equal(got["closest"].view(np.uint8), want["closest"].view(np.uint8))),
                 focal_bit_equal=bool(np.array_equal(bits(got["focalDistances"]), bits(want["focalDistances"]))))
+
+
+def golden_files(prefix):
+    import glob
+    return sorted(glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
+
+
+def rt_params_from_golden(pkg, z, w, h):
+    fp = pkg.default_frame_params(0, w, h)
+    fp.set_camera(z["pos"], z["rot"], float(z["focal"]))
+    aa, soft = int(z["aa"]), int(z["soft"])
+    fp.aaEnabled, fp.aaSamples, fp.softShadowsEnabled = int(aa > 0), max(aa, 1), soft
+    if "soft_samples" in z:
+        fp.softShadowsSamples = int(z["soft_samples"])
+    if "lights" in z:
+        fp.set_lights(z["lights"])
+    fp.set_random_positions(z["table"])
+    return fp
+
+
+def ras_params_from_golden(pkg, z, w, h):
+    fp = pkg.default_frame_params(1, w, h)
+    fp.set_camera(z["pos"], z["rot"], float(z["focal"]))
+    return fp
+
+
+def size_from_name(path):
+    import re
+    m = re.search(r"_(\d+)x(\d+)_", os.path.basename(path))
+    return int(m.group(1)), int(m.group(2))
