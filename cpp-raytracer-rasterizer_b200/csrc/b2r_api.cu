@@ -196,12 +196,6 @@ int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride
     if (count) CU(cudaMemcpyAsync(c->raw.p, triangles, bytes, cudaMemcpyHostToDevice, c->stream), "scene upload");
     c->T = count;
     c->stride = stride;
-    c->hostTris.clear();
-    if (count <= kSmallTris) {
-        c->hostTris.resize((size_t)15 * count);
-        for (int i = 0; i < count; ++i) memcpy(&c->hostTris[(size_t)15 * i], (const char*)triangles + (size_t)i * stride, 60);
-    }
-    c->smallDirty = true;
     // isCulled: byte 60 of the 64-byte rasteriser Triangle; the raytracer Triangle has none
     if (count) {
         if (int rc = ensure_pinned(c, (size_t)count + 64)) return rc;
@@ -285,7 +279,6 @@ int b2r_set_frame(b2r_ctx* ctx, const b2r_frame_params* p) {
         }
     }
     c->params = *p;
-    c->smallDirty = true;
     CU(cudaStreamSynchronize(c->stream), "sync before frame upload");  // pinnedFrame may still be in flight
     memcpy(c->pinnedFrame, &f, sizeof f);
     const size_t used = offsetof(DevFrame, origin) + sizeof(float) * 4 * (size_t)f.nOrigins;

@@ -50,15 +50,6 @@ constexpr int kGeomQuads = 5;
 //   q2..q4 = the three conservative filter forms (see rt_kernels.cu)
 constexpr int kOriginQuads = 5;
 
-// Small-scene path of the raytracer: T <= kSmallTris triangles and at most kSmallMaxOrigins ray origins
-// (camera + light samples).  The conservative filter forms (9 floats per origin and triangle) travel in
-// the kernel-parameter constant bank, so the fully unrolled filter loop reads them as FFMA operands.
-constexpr int kSmallTris = 32;
-constexpr int kSmallMaxOrigins = 17;  // camera + 16 soft-shadow samples of one light
-struct RtSmallConst {
-    float f[kSmallMaxOrigins][kSmallTris][9];
-};
-
 struct RtLaunch {
     const float4* geom;      // T * kGeomQuads
     const DevFrame* frame;
@@ -136,9 +127,6 @@ struct Ctx {
     DevBuf culled;   // T bytes
     DevBuf geom;     // T * 80 bytes (raytracer)
     bool haveScene = false;
-    std::vector<float> hostTris;   // 15 floats per triangle, kept only for scenes that fit the small-scene path
-    RtSmallConst smallConsts{};
-    bool smallDirty = true;
 
     // frame
     b2r_frame_params params{};

@@ -5,8 +5,7 @@
 // pixel, the N x N sub-samples looped in-thread because the reference carries
 // state from one sub-sample to the next, SURVEY.md 8a-1 quirks ii/iii).
 //
-// Structure of one CTA (256 threads, a 32x8 pixel tile per iteration,
-// persistent over tiles):
+// Structure of one CTA (256 threads = 8 warps, each warp an 8x4 pixel tile, persistent over tiles):
 //   1. TMA bulk copy (cp.async.bulk + mbarrier) of the scene-static triangle
 //      records (v0, e1, e2, e1 x e2, normalised normal, colour; float4 rows)
 //      from HBM into shared memory.
@@ -16,24 +15,27 @@
 //      reference operation order, plus three conservative filter forms.
 //      Origin 0 is the camera, origins 1.. are the light sample positions the
 //      shadow rays start from (raytracer.cpp:284-291,310).
-//   3. Per ray and triangle: the FMA filter rejects pairs the reference is
-//      CERTAIN to reject; every other pair runs the reference's arithmetic
-//      literally (non-fused mul/add, IEEE div/sqrt), so accepted hits, the
-//      closest-hit index, positions and distances carry the reference's bits.
+//   3. Culling hierarchy, each level only dropping (ray, triangle) pairs the
+//      reference is CERTAIN to reject:
+//        a. per warp tile: triangles whose filter forms are negative on the
+//           whole tile rectangle (all N*N sub-samples at once);
+//        b. per warp and light sample: triangles that cannot shadow any hit
+//           point of the warp (forms bounded over the box of light->hit vectors);
+//        c. per ray: the three forms evaluated with FMAs.
+//   4. Every surviving pair runs the reference's arithmetic literally (non-fused
+//      mul/add, IEEE div/sqrt), so accepted hits, the closest-hit index, positions
+//      and distances carry the reference's bits.
 //
-// The filter (see setup_origin_triangle): with s = sign((e1 x e2).b), the
-// reference accepts only if s*d1 >= 0, s*d2 >= 0 and s*(d0-d1-d2) >= 0 up to
-// rounding, where d0,d1,d2 are its three dot products with -dir
-// (raytracer.cpp:232-234).  Each is linear in dir, so it is evaluated with
-// two or three FMAs from pre-scaled coefficients and compared against a
-// margin that is >= 4x the worst-case rounding error of BOTH evaluations.
-// A pair is skipped only when one form is below -margin; ties, grazing rays,
-// degenerate triangles and non-finite values all fall through to the exact
-// path.  Switch the filter off with B2R_OPT_RT_FILTER=0: results are
-// identical (tests/test_rt_parity.py checks this).
+// The filter (see filter_forms): with s = sign((e1 x e2).b), the reference accepts
+// only if s*d1 >= 0, s*d2 >= 0 and s*(d0-d1-d2) >= 0 up to rounding, where d0,d1,d2
+// are its three dot products with -dir (raytracer.cpp:232-234).  Each is linear in
+// dir, so it is evaluated with FMAs from pre-scaled coefficients and compared
+// against a margin that is >= 4x the worst-case rounding error of BOTH
+// evaluations.  A pair is skipped only when one form is below -margin; ties,
+// grazing rays, degenerate triangles and non-finite values all fall through to the
+// exact path.  B2R_OPT_RT_FILTER=0 switches every level off: results are identical
+// (tests/test_rt_parity.py checks this).
 #include <float.h>
-
-#include <type_traits>
 
 #include "b2r_internal.h"
 #include "exact.cuh"
@@ -197,23 +199,6 @@ __host__ __device__ inline OriginTri origin_constants(V3 v0, V3 e1, V3 e2, V3 n,
     return o;
 }
 
-// Host side of the small-scene path: filter forms for every (origin, triangle) into the kernel-parameter block.
-void build_small_consts(const float* tris15, int T, const DevFrame& f, RtSmallConst* out) {
-    for (int o = 0; o < f.nOrigins; ++o)
-        for (int i = 0; i < kSmallTris; ++i) {
-            float* dst = out->f[o][i];
-            if (i >= T) {  // padding up to the unroll width; masked off in the kernel
-                for (int k = 0; k < 9; ++k) dst[k] = 0.f;
-                continue;
-            }
-            const float* t = tris15 + 15 * i;
-            const V3 v0 = mk3(t[0], t[1], t[2]), v1 = mk3(t[3], t[4], t[5]), v2 = mk3(t[6], t[7], t[8]);
-            const V3 e1 = xsub3(v1, v0), e2 = xsub3(v2, v0), n = xcross3(e1, e2);
-            const OriginTri c = origin_constants(v0, e1, e2, n, mk3(f.origin[o][0], f.origin[o][1], f.origin[o][2]));
-            filter_forms(n, c.be2, c.e1b, c.nb, o == 0, f.R, f.focal, f.primaryDmax, dst);
-        }
-}
-
 // ---------------------------------------------------------------------------
 // The exact test: ClosestIntersection's loop body, raytracer.cpp:229-252.
 // nd = -dir.  Returns true when the reference accepts the hit; pos/dist valid then.
@@ -244,95 +229,127 @@ struct Counters {
     unsigned long long primary = 0, shadow = 0, exact = 0;
 };
 
-// Shared-memory layout of one CTA.
-struct Smem {
-    const float4* G;  // T * kGeomQuads         scene-static triangle records
-    const float4* X;  // nO * T * 2             exact per-(origin,triangle) constants: (be2, nb), (e1b, 0)
-    const float4* F;  // nO * T * 3             filter forms (generic path only)
-    const float4* org;   // nO ray origins
-    const float4* power; // nLights light powers
-};
-
 constexpr int kTileW = 32, kTileH = 8, kThreads = 256;
+constexpr unsigned kFull = 0xFFFFFFFFu;
 
-// Candidate masks: bit (31 - j) set <=> triangle (base + j) must take the exact path.
-// The three forms are OR-ed as integers: any sign bit set = some form negative = certain reject.
+// ---------------------------------------------------------------------------
+// Hierarchical culling.  All of it only ever removes (ray, triangle) pairs
+// that the per-ray filter would also remove, i.e. pairs the reference is
+// certain to reject; every surviving pair still goes through the per-ray
+// filter and then the exact reference-order test.
+//
+// Primary rays: one warp owns an 8x4 pixel tile.  Every sub-sample of every
+// pixel of the tile has (dx,dy) inside a rectangle [cx-hx, cx+hx]x[cy-hy, cy+hy]
+// (the AA offsets stay within [-0.5, +0.5], raytracer.cpp:564-574,593,596), and
+// each filter form E = B*dx + C*dy + A is linear, so
+//      max over the tile of E  =  E(cx,cy) + |B|*hx + |C|*hy.
+// Lane j evaluates triangle base+j; a triangle whose form maximum is negative
+// is rejected for the whole tile and for all N*N sub-samples at once.
+// ---------------------------------------------------------------------------
 template <bool FILTER>
-__device__ __forceinline__ unsigned primary_candidates_small(const RtSmallConst& k, int T, float dx, float dy) {
-    const unsigned valid = T >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> T);  // entries >= T are padding
-    if (!FILTER) return valid;
-    unsigned rej = 0u;
+__device__ __forceinline__ unsigned primary_tile_mask(const float4* __restrict__ F0, int base, int T, int lane,
+                                                      float cx, float cy, float hx, float hy) {
+    const int i = base + lane;
+    const bool valid = i < T;
+    bool keep = valid;
+    if (FILTER && valid) {
+        const float4* F = F0 + 3 * i;
 #pragma unroll
-    for (int i = 0; i < kSmallTris; ++i) {
-        const float* c = k.f[0][i];  // compile-time offsets: the coefficients are constant-bank operands of the FFMAs
-        const float E1 = fmaf(c[0], dx, fmaf(c[1], dy, c[2]));
-        const float E2 = fmaf(c[3], dx, fmaf(c[4], dy, c[5]));
-        const float E3 = fmaf(c[6], dx, fmaf(c[7], dy, c[8]));
-        rej = __funnelshift_l(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3), rej, 1);
-    }
-    return ~rej & valid;
-}
-
-template <bool FILTER, bool FIXED_ORIGIN>
-__device__ __forceinline__ unsigned shadow_candidates_small(const RtSmallConst& k, int T, int o, V3 r) {
-    const unsigned valid = T >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> T);
-    if (!FILTER) return valid;
-    unsigned rej = 0u;
-    const float(*f)[9] = FIXED_ORIGIN ? k.f[1] : k.f[o];
-#pragma unroll
-    for (int i = 0; i < kSmallTris; ++i) {
-        const float* c = f[i];
-        const float G1 = fmaf(c[0], r.x, fmaf(c[1], r.y, fmaf(c[2], r.z, kShadowMargin)));
-        const float G2 = fmaf(c[3], r.x, fmaf(c[4], r.y, fmaf(c[5], r.z, kShadowMargin)));
-        const float G3 = fmaf(c[6], r.x, fmaf(c[7], r.y, fmaf(c[8], r.z, kShadowMargin)));
-        rej = __funnelshift_l(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3), rej, 1);
-    }
-    return ~rej & valid;
-}
-
-// Generic path: forms in shared memory, a chunk of n <= 32 triangles starting at F (3 float4 per triangle).
-template <bool FILTER, bool PRIMARY>
-__device__ __forceinline__ unsigned candidates_smem(const float4* __restrict__ F, int n, float a, float b, float c3) {
-    const unsigned valid = n >= 32 ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> n);
-    if (!FILTER) return valid;
-    unsigned rej = 0u;
-    for (int i = 0; i < n; ++i, F += 3) {
-        const float4 c1 = F[0], c2 = F[1], c3q = F[2];
-        float E1, E2, E3;
-        if (PRIMARY) {
-            E1 = fmaf(c1.x, a, fmaf(c1.y, b, c1.z));
-            E2 = fmaf(c2.x, a, fmaf(c2.y, b, c2.z));
-            E3 = fmaf(c3q.x, a, fmaf(c3q.y, b, c3q.z));
-        } else {
-            E1 = fmaf(c1.x, a, fmaf(c1.y, b, fmaf(c1.z, c3, kShadowMargin)));
-            E2 = fmaf(c2.x, a, fmaf(c2.y, b, fmaf(c2.z, c3, kShadowMargin)));
-            E3 = fmaf(c3q.x, a, fmaf(c3q.y, b, fmaf(c3q.z, c3, kShadowMargin)));
+        for (int k = 0; k < 3; ++k) {
+            const float4 c = F[k];
+            const float emax = fmaf(fabsf(c.x), hx, fmaf(fabsf(c.y), hy, fmaf(c.x, cx, fmaf(c.y, cy, c.z))));
+            keep = keep && !(emax < 0.f);
         }
-        rej = __funnelshift_l(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3), rej, 1);
     }
-    return ~(rej << (32 - n)) & valid;
+    return __ballot_sync(kFull, keep);
 }
 
-// ---------------------------------------------------------------------------
-// The kernel.  SMALL: T <= 32 and few origins, filter forms in the parameter bank.
-// HARD1: exactly one light and one shadow sample (the reference's default), origin index fixed.
-// ---------------------------------------------------------------------------
-template <bool SMALL>
-using FilterArg = std::conditional_t<SMALL, RtSmallConst, int>;
+// Per-ray filter over the triangles of a tile mask (bit j <-> triangle base+j).
+template <bool FILTER>
+__device__ __forceinline__ unsigned primary_ray_mask(const float4* __restrict__ F0, int base, unsigned tileMask,
+                                                     float dx, float dy) {
+    if (!FILTER) return tileMask;
+    unsigned m = 0u;
+    for (unsigned tm = tileMask; tm; tm &= tm - 1) {  // warp-uniform loop
+        const int j = __ffs(tm) - 1;
+        const float4* F = F0 + 3 * (base + j);
+        const float4 c1 = F[0], c2 = F[1], c3 = F[2];
+        const float E1 = fmaf(c1.x, dx, fmaf(c1.y, dy, c1.z));
+        const float E2 = fmaf(c2.x, dx, fmaf(c2.y, dy, c2.z));
+        const float E3 = fmaf(c3.x, dx, fmaf(c3.y, dy, c3.z));
+        // any sign bit set = some form negative = certain reject
+        if ((int)(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3)) >= 0) m |= 1u << j;
+    }
+    return m;
+}
 
-template <bool SMALL, bool HARD1, bool FILTER, bool STATS>
-__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a,
-                                                                  const __grid_constant__ FilterArg<SMALL> fa) {
+// Shadow rays of one light sample: q = lightPos - hitPos per lane, rDir = q/|q|.  The per-ray forms are
+// G_k(rDir) = g_k.rDir + 1.0001 >= 0, equivalently g_k.q + 1.0001*|q| >= 0.  Over the warp's bounding box
+// [qlo,qhi] of q and with rb >= |q| for every lane, the form is at most
+//      sum_j max(g_kj*qlo_j, g_kj*qhi_j) + 1.0001*rb ;
+// a triangle for which some form's bound is negative cannot pass the per-ray filter on any lane.
+template <bool FILTER>
+__device__ __forceinline__ unsigned shadow_warp_mask(const float4* __restrict__ Fo, int base, int T, int lane,
+                                                     V3 qlo, V3 qhi, float rb) {
+    const int i = base + lane;
+    const bool valid = i < T;
+    bool keep = valid;
+    if (FILTER && valid) {
+        const float4* F = Fo + 3 * i;
+        const float slack = kShadowMargin * rb;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 g = F[k];
+            const float ub = fmaxf(g.x * qlo.x, g.x * qhi.x) + fmaxf(g.y * qlo.y, g.y * qhi.y) +
+                             fmaxf(g.z * qlo.z, g.z * qhi.z) + slack;
+            keep = keep && !(ub < 0.f);
+        }
+    }
+    return __ballot_sync(kFull, keep);
+}
+
+template <bool FILTER>
+__device__ __forceinline__ unsigned shadow_ray_mask(const float4* __restrict__ Fo, int base, unsigned warpMask, V3 r) {
+    if (!FILTER) return warpMask;
+    unsigned m = 0u;
+    for (unsigned tm = warpMask; tm; tm &= tm - 1) {
+        const int j = __ffs(tm) - 1;
+        const float4* F = Fo + 3 * (base + j);
+        const float4 c1 = F[0], c2 = F[1], c3 = F[2];
+        const float G1 = fmaf(c1.x, r.x, fmaf(c1.y, r.y, fmaf(c1.z, r.z, kShadowMargin)));
+        const float G2 = fmaf(c2.x, r.x, fmaf(c2.y, r.y, fmaf(c2.z, r.z, kShadowMargin)));
+        const float G3 = fmaf(c3.x, r.x, fmaf(c3.y, r.y, fmaf(c3.z, r.z, kShadowMargin)));
+        if ((int)(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3)) >= 0) m |= 1u << j;
+    }
+    return m;
+}
+
+// Order-preserving float <-> int map so warp min/max can use the integer REDUX unit.
+__device__ __forceinline__ int f2ord(float f) {
+    const int k = __float_as_int(f);
+    return k ^ ((k >> 31) & 0x7FFFFFFF);
+}
+__device__ __forceinline__ float ord2f(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7FFFFFFF)); }
+__device__ __forceinline__ float warp_min(float v) { return ord2f(__reduce_min_sync(kFull, f2ord(v))); }
+__device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(kFull, f2ord(v))); }
+
+// ---------------------------------------------------------------------------
+// The kernel.  TILECULL = false keeps only the per-ray filter (every ray looks at every triangle).
+// ---------------------------------------------------------------------------
+template <bool TILECULL, bool FILTER, bool STATS>
+__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
     const DevFrame* __restrict__ f = a.frame;
     const int nO = f->nOrigins;
-    float4* sG = reinterpret_cast<float4*>(smem_raw);        // T * kGeomQuads
-    float4* sX = sG + (size_t)T * kGeomQuads;                // nO * T * 2
-    float4* sOrg = sX + (size_t)nO * T * 2;                  // nO
-    float4* sPow = sOrg + nO;                                // nLights
-    float4* sF = sPow + f->nLights;                          // nO * T * 3 (generic path only)
+    const int nChunks = (T + 31) >> 5;
+    float4* sG = reinterpret_cast<float4*>(smem_raw);        // T * kGeomQuads   scene-static triangle records
+    float4* sX = sG + (size_t)T * kGeomQuads;                // nO * T * 2       exact (origin,triangle) constants
+    float4* sF = sX + (size_t)nO * T * 2;                    // nO * T * 3       filter forms
+    float4* sOrg = sF + (size_t)nO * T * 3;                  // nO               ray origins
+    float4* sPow = sOrg + nO;                                // nLights          light powers
+    unsigned* sTileMask = reinterpret_cast<unsigned*>(sPow + f->nLights);  // 8 warps * nChunks
 
     // 1. triangles: HBM -> shared memory by one bulk async copy (TMA), completion on an mbarrier
     const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
@@ -360,7 +377,7 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
         const OriginTri c = origin_constants(t.v0, t.e1, t.e2, t.n, mk3(og.x, og.y, og.z));
         sX[2 * it] = make_float4(c.be2.x, c.be2.y, c.be2.z, c.nb);
         sX[2 * it + 1] = make_float4(c.e1b.x, c.e1b.y, c.e1b.z, 0.f);
-        if (!SMALL && FILTER) {
+        if (FILTER) {
             float q[9];
             filter_forms(t.n, c.be2, c.e1b, c.nb, o == 0, f->R, f->focal, f->primaryDmax, q);
             sF[3 * it] = make_float4(q[0], q[1], q[2], 0.f);
@@ -376,20 +393,38 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
     for (int i = 0; i < 9; ++i) R[i] = f->R[i];
     const float focalLength = f->focal, dofFocal = f->dofFocal;
     const V3 indirect = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
-    const int N = f->aaN;
-    const int nLights = HARD1 ? 1 : f->nLights, samples = HARD1 ? 1 : f->samples;
+    const int N = f->aaN, nLights = f->nLights, samples = f->samples;
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
     const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
     const float invNN = (float)(N * N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned* myTileMask = sTileMask + warp * nChunks;
     Counters cnt;
+    unsigned tile0 = 0u;  // tile mask of the only chunk when T <= 32
 
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
-        const int x = tx * kTileW + (warp & 3) * 8 + (lane & 7);
-        const int y = a.y0 + ty * kTileH + (warp >> 2) * 4 + (lane >> 3);
-        if (x >= a.W || y >= a.y1) continue;
+        const int wx0 = tx * kTileW + (warp & 3) * 8, wy0 = a.y0 + ty * kTileH + (warp >> 2) * 4;
+        const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
+        const bool inside = x < a.W && y < a.y1;  // lanes outside stay for the warp collectives
+        if (!__any_sync(kFull, inside)) continue;
+
+        // tile-level candidate masks for the primary rays of all sub-samples
+        {
+            // sub-sample coordinates lie in [x-0.5, x+0.5] (AA) or are exactly x; pad for rounding
+            const float pad = (N > 1) ? 0.5f + 0.01f : 0.01f;
+            const float cx = ((float)wx0 + 3.5f) - halfW, cy = ((float)wy0 + 1.5f) - halfH;
+            const float hx = 3.5f + pad, hy = 1.5f + pad;
+            for (int c = 0; c < nChunks; ++c) {
+                unsigned m;
+                if (TILECULL) m = primary_tile_mask<FILTER>(sF, c * 32, T, lane, cx, cy, hx, hy);
+                else m = (T - c * 32 >= 32) ? kFull : ((1u << (T - c * 32)) - 1u);
+                if (nChunks > 1 && lane == 0) myTileMask[c] = m;
+                if (nChunks == 1) tile0 = m;
+            }
+            if (nChunks > 1) __syncwarp();
+        }
 
         PixelState ps;  // Update()'s per-frame reset, raytracer.cpp:335-339 (+P5)
         ps.pos = mk3(0.f, 0.f, 0.f);
@@ -406,72 +441,90 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
                 const V3 dir = xmat_vec(R, mk3(dx, dy, focalLength));
                 const V3 nd = neg3(dir);  // :229
                 bool any = false;
-                if constexpr (STATS) cnt.primary++;
-                for (int base = 0; base < T; base += 32) {
-                    unsigned cand;
-                    if constexpr (SMALL) cand = primary_candidates_small<FILTER>(fa, T, dx, dy);
-                    else cand = candidates_smem<FILTER, true>(sF + 3 * base, min(32, T - base), dx, dy, 0.f);
-                    while (cand) {  // ascending triangle index = descending bit
-                        const int j = __clz(cand);
-                        cand &= ~(0x80000000u >> j);
-                        const int i = base + j;
-                        if constexpr (STATS) cnt.exact++;
-                        V3 pos;
-                        float dist;
-                        if (exact_hit(sG + i * kGeomQuads, sX + 2 * i, cam, nd, pos, dist)) {
-                            if (ps.dist >= dist) {  // :243 ties -> later index
-                                ps.pos = pos;
-                                ps.dist = dist;
-                                ps.idx = i;
-                                ps.focal = xsub(dist, dofFocal);  // :249
+                if (inside) {
+                    if constexpr (STATS) cnt.primary++;
+                    for (int c = 0; c < nChunks; ++c) {
+                        const int base = c * 32;
+                        const unsigned tm = (nChunks > 1) ? myTileMask[c] : tile0;
+                        unsigned m = primary_ray_mask<FILTER>(sF, base, tm, dx, dy);
+                        for (; m; m &= m - 1) {  // ascending triangle index
+                            const int i = base + __ffs(m) - 1;
+                            if constexpr (STATS) cnt.exact++;
+                            V3 pos;
+                            float dist;
+                            if (exact_hit(sG + i * kGeomQuads, sX + 2 * i, cam, nd, pos, dist)) {
+                                if (ps.dist >= dist) {  // :243 ties -> later index
+                                    ps.pos = pos;
+                                    ps.dist = dist;
+                                    ps.idx = i;
+                                    ps.focal = xsub(dist, dofFocal);  // :249
+                                }
+                                any = true;  // :251
                             }
-                            any = true;  // :251
                         }
                     }
                 }
-                if (any) {
-                    // ---- DirectLight :265-327
-                    const float4 g3 = sG[ps.idx * kGeomQuads + 3], g4 = sG[ps.idx * kGeomQuads + 4];
-                    const V3 nDir = mk3(g3.x, g3.y, g3.z);
-                    const V3 colr = mk3(g3.w, g4.x, g4.y);
+                // ---- DirectLight :265-327.  The warp stays converged so the shadow rays of all its
+                // hit pixels can be culled together; lanes without a hit only take part in the collectives.
+                if (__any_sync(kFull, any)) {
+                    V3 nDir = mk3(0.f, 0.f, 0.f), colr = mk3(0.f, 0.f, 0.f);
+                    if (any) {
+                        const float4 g3 = sG[ps.idx * kGeomQuads + 3], g4 = sG[ps.idx * kGeomQuads + 4];
+                        nDir = mk3(g3.x, g3.y, g3.z);
+                        colr = mk3(g3.w, g4.x, g4.y);
+                    }
                     V3 result = mk3(0.f, 0.f, 0.f), result2 = mk3(0.f, 0.f, 0.f);
                     for (int k = 0; k < nLights; ++k) {
                         const float4 pw = sPow[k];
                         const V3 P = mk3(pw.x, pw.y, pw.z);  // (color*intensity)/samples :282,296
                         for (int s = 0; s < samples; ++s) {
-                            const int o = HARD1 ? 1 : 1 + k * samples + s;
+                            const int o = 1 + k * samples + s;
                             const float4 og = sOrg[o];
                             const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
                             const V3 dv = xsub3(lpos, ps.pos);       // position - i.position
                             const float rr = xdot3(dv, dv);
                             const float r = xsqrt(rr);               // :294
-                            const float A = sphere_area(r);          // :295
                             const V3 rDir = xscale3(dv, xdiv(1.0f, r));  // :298 normalize
-                            const V3 B = xdivs3(P, A);               // :301
-                            V3 D = xscale3(B, std_max(xdot3(rDir, nDir), 0.0f));  // :304
+                            V3 D = mk3(0.f, 0.f, 0.f);
+                            if (any) {
+                                const float A = sphere_area(r);      // :295
+                                const V3 B = xdivs3(P, A);           // :301
+                                D = xscale3(B, std_max(xdot3(rDir, nDir), 0.0f));  // :304
+                                if constexpr (STATS) cnt.shadow++;
+                            }
                             // ---- shadow ray from the light towards the surface :307-315
                             // direction -rDir, so -dir == rDir; occluded iff any accepted hit is
                             // closer than r*0.99f (== j.distance < r*0.99f, j the closest hit)
                             const float thr = xmul(r, 0.99f);
                             bool occluded = false;
-                            if constexpr (STATS) cnt.shadow++;
                             const float4* xs = sX + (size_t)2 * o * T;
-                            for (int base = 0; base < T && !occluded; base += 32) {
-                                unsigned cand;
-                                if constexpr (SMALL) cand = shadow_candidates_small<FILTER, HARD1>(fa, T, o, rDir);
-                                else
-                                    cand = candidates_smem<FILTER, false>(sF + 3 * ((size_t)o * T + base),
-                                                                          min(32, T - base), rDir.x, rDir.y, rDir.z);
-                                while (cand) {
-                                    const int j = __clz(cand);
-                                    cand &= ~(0x80000000u >> j);
-                                    const int i = base + j;
-                                    if constexpr (STATS) cnt.exact++;
-                                    V3 pos;
-                                    float dist;
-                                    if (exact_hit(sG + i * kGeomQuads, xs + 2 * i, lpos, rDir, pos, dist) && dist < thr) {
-                                        occluded = true;
-                                        break;
+                            const float4* Fo = sF + (size_t)3 * o * T;
+                            V3 qlo = mk3(0.f, 0.f, 0.f), qhi = mk3(0.f, 0.f, 0.f);
+                            float rb = 0.f;
+                            if (TILECULL && FILTER) {
+                                const float big = 3.0e38f;
+                                qlo = mk3(warp_min(any ? dv.x : big), warp_min(any ? dv.y : big), warp_min(any ? dv.z : big));
+                                qhi = mk3(warp_max(any ? dv.x : -big), warp_max(any ? dv.y : -big), warp_max(any ? dv.z : -big));
+                                const float mx = fmaxf(fabsf(qlo.x), fabsf(qhi.x)), my = fmaxf(fabsf(qlo.y), fabsf(qhi.y)),
+                                            mz = fmaxf(fabsf(qlo.z), fabsf(qhi.z));
+                                rb = sqrtf(fmaf(mx, mx, fmaf(my, my, mz * mz))) * 1.00001f;
+                            }
+                            for (int c = 0; c < nChunks; ++c) {
+                                const int base = c * 32;
+                                unsigned wm;
+                                if (TILECULL) wm = shadow_warp_mask<FILTER>(Fo, base, T, lane, qlo, qhi, rb);
+                                else wm = (T - base >= 32) ? kFull : ((1u << (T - base)) - 1u);
+                                if (any && !occluded) {
+                                    unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir);
+                                    for (; m; m &= m - 1) {
+                                        const int i = base + __ffs(m) - 1;
+                                        if constexpr (STATS) cnt.exact++;
+                                        V3 pos;
+                                        float dist;
+                                        if (exact_hit(sG + i * kGeomQuads, xs + 2 * i, lpos, rDir, pos, dist) && dist < thr) {
+                                            occluded = true;
+                                            break;
+                                        }
                                     }
                                 }
                             }
@@ -480,30 +533,34 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
                         }
                         result2 = xadd3(result2, result);   // :322 (result is not reset per light)
                     }
-                    const V3 color = xmul3(result2, colr);  // :325-326
-                    const V3 Tsum = xadd3(color, indirect); // :586
-                    avg = xadd3(avg, xmul3(colr, Tsum));    // :587-591
-                    x1 = xadd(x1, stepAA);                  // :593 -- only after a hit
+                    if (any) {
+                        const V3 color = xmul3(result2, colr);  // :325-326
+                        const V3 Tsum = xadd3(color, indirect); // :586
+                        avg = xadd3(avg, xmul3(colr, Tsum));    // :587-591
+                        x1 = xadd(x1, stepAA);                  // :593 -- only after a hit
+                    }
                 }
             }
             y1 = xadd(y1, stepAA);  // :596
         }
-        avg = xdivs3(avg, invNN);  // :599
-        const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;  // P2: row stride = width
-        if (a.colours) {
-            a.colours[3 * idx] = avg.x;
-            a.colours[3 * idx + 1] = avg.y;
-            a.colours[3 * idx + 2] = avg.z;
+        if (inside) {
+            avg = xdivs3(avg, invNN);  // :599
+            const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;  // P2: row stride = width
+            if (a.colours) {
+                a.colours[3 * idx] = avg.x;
+                a.colours[3 * idx + 1] = avg.y;
+                a.colours[3 * idx + 2] = avg.z;
+            }
+            if (a.closest) {
+                b2r_intersection* c = a.closest + idx;
+                c->position[0] = ps.pos.x;
+                c->position[1] = ps.pos.y;
+                c->position[2] = ps.pos.z;
+                c->distance = ps.dist;
+                c->triangleIndex = ps.idx;
+            }
+            if (a.focal) a.focal[idx] = ps.focal;
         }
-        if (a.closest) {
-            b2r_intersection* c = a.closest + idx;
-            c->position[0] = ps.pos.x;
-            c->position[1] = ps.pos.y;
-            c->position[2] = ps.pos.z;
-            c->distance = ps.dist;
-            c->triangleIndex = ps.idx;
-        }
-        if (a.focal) a.focal[idx] = ps.focal;
     }
 
     if constexpr (STATS) {
@@ -511,20 +568,21 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             unsigned long long s = v[k];
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
             if (lane == 0 && s) atomicAdd(a.stats + k, s);
         }
     }
 }
 
-static size_t rt_smem_bytes(int T, int nO, int nLights, bool withForms) {
-    return ((size_t)T * kGeomQuads + (size_t)nO * T * (withForms ? 5 : 2) + nO + nLights) * 16;
+static size_t rt_smem_bytes(int T, int nO, int nLights) {
+    const size_t quads = (size_t)T * kGeomQuads + (size_t)nO * T * 5 + nO + nLights;
+    return quads * 16 + (size_t)(kThreads / 32) * ((T + 31) / 32) * 4 + 16;
 }
 
-template <bool SMALL, bool HARD1>
-static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, const FilterArg<SMALL>& fa, size_t smem, cudaStream_t s) {
-    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<SMALL, HARD1, true, true> : rt_trace_shade_kernel<SMALL, HARD1, true, false>)
-                            : (a.stats ? rt_trace_shade_kernel<SMALL, HARD1, false, true> : rt_trace_shade_kernel<SMALL, HARD1, false, false>);
+template <bool TILECULL>
+static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<TILECULL, true, true> : rt_trace_shade_kernel<TILECULL, true, false>)
+                            : (a.stats ? rt_trace_shade_kernel<TILECULL, false, true> : rt_trace_shade_kernel<TILECULL, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSM = 1;
@@ -534,29 +592,17 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, const FilterArg<SMA
     int grid = c->smCount * perSM;
     if (grid > a.numTiles) grid = a.numTiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<grid, kThreads, smem, s>>>(a, fa);
+    kern<<<grid, kThreads, smem, s>>>(a);
     c->launches++;
     return cudaGetLastError();
 }
 
-// Variant selection (B2R_OPT_RT_VARIANT): 0 = automatic (small-scene path when it applies), 1 = force generic.
+// B2R_OPT_RT_VARIANT: 0 = tile/warp culling + per-ray filter (default); 1 = per-ray filter only.
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
     const DevFrame& f = c->hostFrame;
-    const bool small = c->optRtVariant != 1 && a.T <= kSmallTris && f.nOrigins <= kSmallMaxOrigins &&
-                       (int)c->hostTris.size() == 15 * a.T;
-    const bool hard1 = f.nLights == 1 && f.samples == 1;
-    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, !small);
+    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights);
     if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;  // reported as B2R_E_UNSUPPORTED by the caller
-    if (small) {
-        if (c->smallDirty) {
-            build_small_consts(c->hostTris.data(), a.T, f, &c->smallConsts);
-            c->smallDirty = false;
-        }
-        return hard1 ? launch_variant<true, true>(c, a, c->smallConsts, smem, s)
-                     : launch_variant<true, false>(c, a, c->smallConsts, smem, s);
-    }
-    const int none = 0;
-    return hard1 ? launch_variant<false, true>(c, a, none, smem, s) : launch_variant<false, false>(c, a, none, smem, s);
+    return c->optRtVariant == 1 ? launch_variant<false>(c, a, smem, s) : launch_variant<true>(c, a, smem, s);
 }
 
 }  // namespace b2r
