@@ -124,7 +124,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -222,9 +222,15 @@ def run_gpu_arm(args, pkg):
             barrier()
         return sum(a.elapsed_time(b) for a, b in evs)  # ms over all steps, device time
 
+    # clocks are sampled from before the warm-up to after the timed loop (nvidia-smi needs ~100 ms to start;
+    # the extra warm-up frames below keep the GPU under the same load while it does)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_end = time.perf_counter() + 0.4
+        while time.perf_counter() < t_end:
+            frame_device()
+        torch.cuda.synchronize(dev)
     launches0 = ctx.launch_count()
     total_ms = timed_loop(frame_device, args.steps, args.warmup)
     launches = ctx.launch_count() - launches0 - 2 * args.warmup
@@ -390,7 +396,7 @@ def other_configs(pkg, torch, dev, stream, flush, local):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2r", choices=["b2r", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")

@@ -1,0 +1,154 @@
+// raytracer_dropin.cpp -- see raytracer_dropin.h.  Host C++ only; all rendering is in libb2r.so.
+#include "raytracer_dropin.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/b2r.h"
+
+namespace rtref {
+
+std::vector<Triangle> triangles;
+bool AA_ENABLED = false;
+int AA_SAMPLES = 3;
+bool SOFT_SHADOWS_ENABLED = false;
+int SOFT_SHADOWS_SAMPLES = 16;
+bool DOF_ENABLED = false;
+int DOF_KERNEL_SIZE = 8;
+float FOCAL_LENGTH = 1.3f;
+int NUM_LIGHTS = 0;
+Light lights[32];
+int SCREEN_WIDTH = 500, SCREEN_HEIGHT = 500;
+float focalLength = 250.0f;
+vec3 cameraPos(0.0f, 0.0f, -2.0f);
+mat3 cameraRot = mat3(0.0f);
+float yaw = 0.0f;
+bool isUpdated = true;
+vec3 indirectLight = 0.2f * vec3(1, 1, 1);
+vec3 randomPositions[256];
+std::vector<float> focalDistances;
+std::vector<vec3> pixelColours;
+std::vector<Intersection> closestIntersections;
+std::vector<uint32_t> screenPixels;
+
+namespace {
+b2r_ctx* g_ctx = nullptr;
+const Triangle* g_uploaded = nullptr;
+size_t g_uploadedCount = 0;
+int g_rc = 0;
+float RandomNumber() { return ((double)rand() / (RAND_MAX)) - 0.5f; }  // :260-263
+}  // namespace
+
+const char* LastError() { return b2r_last_error(g_ctx); }
+
+int Initialize(int width, int height, int device) {
+    Shutdown();
+    SCREEN_WIDTH = width;
+    SCREEN_HEIGHT = height;
+    focalLength = (float)height / 2.0f;  // 250 at the reference's 500x500 (:69)
+    const size_t n = (size_t)width * height;
+    focalDistances.assign(n, 0.0f);
+    pixelColours.assign(n, vec3());
+    screenPixels.assign(n, 0u);
+    Intersection init;
+    init.position = vec3();
+    init.distance = 3.402823466e+38f;  // numeric_limits<float>::max(), :153-160
+    init.triangleIndex = -1;
+    closestIntersections.assign(n, init);
+    cameraRot = mat3(0.0f);
+    cameraRot[1][1] = 1.0f;  // :162
+    NUM_LIGHTS = 0;
+    AddLight(vec3(0, -0.5f, -0.7f), vec3(1, 1, 1), 14);  // :116
+    LoadTestModel(triangles);                            // :149
+    g_uploaded = nullptr;
+    isUpdated = true;
+    return g_rc = b2r_create(&g_ctx, device, width, height);
+}
+
+void Shutdown() {
+    if (g_ctx) b2r_destroy(g_ctx);
+    g_ctx = nullptr;
+}
+
+void LoadTestModel(std::vector<Triangle>& out) {
+    static_assert(sizeof(Triangle) == 60, "raytracer Triangle");
+    out.clear();
+    out.reserve(30);
+    unsigned char raw[30 * 60];
+    const int n = b2r_scene_cornell_box(raw, 30, 60);
+    for (int i = 0; i < n; ++i) {
+        Triangle t(vec3(0, 0, 0), vec3(0, 0, 0), vec3(0, 0, 0), vec3(0, 0, 0));
+        std::memcpy(&t, raw + 60 * i, 60);
+        out.push_back(t);
+    }
+}
+
+void AddLight(vec3 position, vec3 color, float intensity) {
+    lights[NUM_LIGHTS].position = position;
+    lights[NUM_LIGHTS].color = color;
+    lights[NUM_LIGHTS].intensity = intensity;
+    for (int i = 0; i < SOFT_SHADOWS_SAMPLES; i++) {
+        // constructor arguments of :188; g++ evaluates them last to first
+        const float rz = RandomNumber(), ry = RandomNumber(), rx = RandomNumber();
+        randomPositions[(NUM_LIGHTS * SOFT_SHADOWS_SAMPLES) + i] =
+            vec3(position.x + (rx * 0.08f), position.y + (ry * 0.08f), position.z + (rz * 0.08f));
+    }
+    NUM_LIGHTS++;
+}
+
+void DeleteLight() {
+    if (NUM_LIGHTS > 0) NUM_LIGHTS--;
+}
+
+void Update() {
+    // :335-339 resets every Intersection to distance FLT_MAX: b2r_rt_frame does that on the device.
+    const float c = std::cos(yaw), s = std::sin(yaw);  // :377-382
+    cameraRot[0][0] = c;
+    cameraRot[0][2] = s;
+    cameraRot[2][0] = -s;
+    cameraRot[2][2] = c;
+}
+
+void Draw() {
+    if (!g_ctx) {
+        g_rc = B2R_E_NO_SCENE;
+        return;
+    }
+    // the scene is (re)uploaded only when the global vector changed
+    if (g_uploaded != triangles.data() || g_uploadedCount != triangles.size()) {
+        g_rc = b2r_set_triangles(g_ctx, triangles.data(), (int)triangles.size(), (int)sizeof(Triangle));
+        if (g_rc) return;
+        g_uploaded = triangles.data();
+        g_uploadedCount = triangles.size();
+    }
+    b2r_frame_params p;
+    std::memset(&p, 0, sizeof p);
+    std::memcpy(p.cameraPos, &cameraPos, 12);
+    std::memcpy(p.cameraRot, &cameraRot, 36);
+    p.focalLength = focalLength;
+    p.numLights = NUM_LIGHTS;
+    std::memcpy(p.lights, lights, sizeof(Light) * 32);
+    std::memcpy(p.randomPositions, randomPositions, sizeof randomPositions);
+    p.aaEnabled = AA_ENABLED;
+    p.aaSamples = AA_SAMPLES;
+    p.softShadowsEnabled = SOFT_SHADOWS_ENABLED;
+    p.softShadowsSamples = SOFT_SHADOWS_SAMPLES;
+    std::memcpy(p.indirectLight, &indirectLight, 12);
+    p.dofFocalLength = FOCAL_LENGTH;
+    p.dofEnabled = DOF_ENABLED;
+    p.dofKernelSize = DOF_KERNEL_SIZE;
+    p.currentReflectance[0] = p.currentReflectance[1] = p.currentReflectance[2] = 1.0f;
+    if ((g_rc = b2r_set_frame(g_ctx, &p)) != 0) return;
+    g_rc = b2r_rt_frame(g_ctx, screenPixels.data(), reinterpret_cast<float*>(pixelColours.data()),
+                        reinterpret_cast<b2r_intersection*>(closestIntersections.data()), focalDistances.data());
+}
+
+int SaveBMP(const char* path) {
+    if (!g_ctx) return B2R_E_NO_SCENE;
+    std::vector<uint8_t> bgr(b2r_bmp_payload_bytes(SCREEN_WIDTH, SCREEN_HEIGHT));
+    int rc = b2r_resolve_bgr8(g_ctx, bgr.data());
+    if (rc) return rc;
+    return b2r_write_bmp(path, bgr.data(), SCREEN_WIDTH, SCREEN_HEIGHT);
+}
+
+}  // namespace rtref

@@ -1,0 +1,107 @@
+"""C-ABI checks that need no GPU: the library loads, exports every declared symbol, structs match, host helpers work."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT, fnv1a32
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.load_library()
+    header = open(os.path.join(ROOT, "include", "b2r.h")).read()
+    declared = sorted(set(re.findall(r"\b(b2r_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"libb2r.so does not export {name}"
+    assert sorted(pkg.capi.SYMBOLS) == declared, "capi.SYMBOLS out of sync with include/b2r.h"
+    assert lib.b2r_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(pkg, tmp_path):
+    """sizeof/offsetof as the C compiler sees them == the ctypes mirror."""
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b2r.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   "sizeof(b2r_frame_params),sizeof(b2r_light),sizeof(b2r_intersection),offsetof(b2r_frame_params,randomPositions),"
+                   "offsetof(b2r_frame_params,aaEnabled),offsetof(b2r_frame_params,currentReflectance));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    FP = pkg.FrameParams
+    assert got == [C.sizeof(FP), C.sizeof(pkg.capi.Light), 20, FP.randomPositions.offset, FP.aaEnabled.offset,
+                   FP.currentReflectance.offset]
+    assert C.sizeof(pkg.capi.Light) == 28  # == reference Light (TestModel.h:35-45)
+
+
+def test_cornell_box_fingerprint(pkg):
+    t = pkg.cornell_box()
+    assert t.shape == (30, 15)
+    assert "%08x" % fnv1a32(t.tobytes()) == "b715a8a2"  # FNV-1a32 over the 30 x 60-byte Triangles
+    # 64-byte flavour: same 60 bytes + isCulled = 0
+    buf = np.zeros(30 * 64, np.uint8)
+    assert pkg.load_library().b2r_scene_cornell_box(buf.ctypes.data_as(C.c_void_p), 30, 64) == 30
+    rec = buf.reshape(30, 64)
+    assert np.array_equal(rec[:, :60].copy().view(np.float32).reshape(30, 15), t) and not rec[:, 60:].any()
+    assert pkg.load_library().b2r_scene_cornell_box(buf.ctypes.data_as(C.c_void_p), 29, 64) < 0
+
+
+def test_tessellation(pkg):
+    t = pkg.cornell_box()
+    assert np.array_equal(pkg.tessellate(t, 1), t)
+    for k in (2, 5):
+        tt = pkg.tessellate(t, k)
+        assert len(tt) == 30 * k * k
+        # colours inherited, normals unit length, total area preserved
+        assert np.array_equal(np.unique(tt[:, 12:15], axis=0), np.unique(t[:, 12:15], axis=0))
+        assert np.allclose(np.linalg.norm(tt[:, 9:12], axis=1), 1, atol=1e-5)
+        area = lambda a: 0.5 * np.linalg.norm(np.cross(a[:, 3:6] - a[:, 0:3], a[:, 6:9] - a[:, 0:3]), axis=1).sum()
+        assert abs(area(tt) - area(t)) < 1e-3
+    assert pkg.load_library().b2r_scene_tessellate(t.ctypes.data_as(C.c_void_p), 30, 60, 183, None, 60) == 1004670
+
+
+def test_default_params_and_cameras(pkg):
+    fp = pkg.default_frame_params(0, 500, 500)
+    assert (fp.focalLength, fp.cameraPos[2], fp.numLights, fp.lights[0].intensity) == (250.0, -2.0, 1, 14.0)
+    assert list(fp.cameraRot) == [1, 0, 0, 0, 1, 0, 0, 0, 1] and fp.aaSamples == 3 and fp.softShadowsSamples == 16
+    fp = pkg.default_frame_params(1, 500, 500)
+    assert (fp.focalLength, fp.cameraPos[2]) == (500.0, -3.0) and abs(fp.cameraRot[4] - 1.01) < 1e-7
+    assert fp.backfaceCulling == 1 and fp.frustumCulling == 1
+    pos, rot = pkg.orbit_camera(90, 360)
+    assert np.allclose(pos, [2, 0, 0], atol=1e-6) and np.allclose(rot.reshape(3, 3)[2], [-1, 0, 0], atol=1e-6)
+    tab = pkg.jitter_table(1, [0, -0.5, -0.7])
+    assert np.abs(tab[:16] - np.array([0, -0.5, -0.7], np.float32)).max() <= 0.04 + 1e-6 and not tab[16:].any()
+
+
+def test_bmp_writer(pkg, tmp_path):
+    w, h = 5, 3  # 15 bytes per row -> pitch 16
+    payload = np.arange(16 * 3, dtype=np.uint8)
+    path = str(tmp_path / "t.bmp")
+    pkg.write_bmp(path, payload, w, h)
+    raw = open(path, "rb").read()
+    assert len(raw) == 54 + 48 and raw[:2] == b"BM"
+    assert int.from_bytes(raw[2:6], "little") == 102 and int.from_bytes(raw[10:14], "little") == 54
+    assert int.from_bytes(raw[28:30], "little") == 24 and raw[54:] == payload.tobytes()
+    assert pkg.load_library().b2r_bmp_payload_bytes(500, 500) == 750000  # the shipped screenshots: 750,054 bytes
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a GPU the product refuses to run instead of silently rendering on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.B2RError, match="no CPU fallback"):
+        pkg.Context(64, 64)
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under the package directory may import, link or mention the oracle as a dependency."""
+    pkg_dir = os.path.join(ROOT, "cpp-raytracer-rasterizer_b200")
+    for d, _, files in os.walk(pkg_dir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                text = open(os.path.join(d, f)).read()
+                assert "liboracle" not in text and "portbind" not in text and "refbind" not in text, os.path.join(d, f)
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), os.path.join(d, f)
