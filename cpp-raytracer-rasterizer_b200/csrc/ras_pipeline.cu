@@ -1,4 +1,4 @@
-// ras_kernels.cu -- the rasteriser hot path on sm_100a.
+// ras_pipeline.cu -- the rasteriser hot path on sm_100a.
 //
 // Replaces Draw() -> DrawPolygon() -> VertexShader / ComputePolygonRows /
 // Interpolate / DrawRows / DrawLineSDL / Bresenham / PixelShader of
@@ -14,18 +14,27 @@
 // the winner (PixelShader's writes are simply overwritten by later winners in
 // the reference, so shading only the final one gives identical arrays).
 //
-// Stages (all arithmetic in reference order, non-fused):
-//   ras_setup     1 thread / triangle: VertexShader x3, minY, ROWS, edge sample counts
-//   scan          exclusive prefix sums (rows, edge samples) -> buffer offsets
-//   ras_edges     1 thread / (triangle, edge): Interpolate's serial float
-//                 accumulation, replayed step by step (it decides coverage via
-//                 int(current.x) and the zinv values the depth test compares)
-//   ras_rows      1 warp / 32 polygon rows: left/right resolve with the
-//                 reference's strict < / > rules in edge order, then the row's
-//                 fragments -> atomicMax on the key buffer; short rows per lane,
-//                 long rows cooperatively across the warp
-//   ras_shade     1 thread / pixel: winner's attributes recomputed from its row
-//                 record, PixelShader, outputs
+// All arithmetic that decides coverage, depth or colour is in reference order,
+// non-fused.  Interpolate's serial float accumulation along each edge (:632-635)
+// decides both coverage (via int(current.x)) and the zinv values compared in the
+// depth test, so it is replayed step by step, never re-associated.
+//
+// Pipeline (v2):
+//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 24 rows
+//                 (the 1M-triangle regime) are finished here: the three edge walks
+//                 (x and zinv chains only) update per-row left/right ends kept in
+//                 shared memory, then every on-screen fragment goes to the key
+//                 buffer with atomicMax -- no per-triangle, per-edge or per-row
+//                 intermediate ever reaches HBM.  Larger triangles are appended to
+//                 a compact list (setup record + row/edge-sample counts).
+//   big path      only for the listed large triangles: exclusive scan of the counts,
+//                 ras_edges (1 thread / triangle-edge, stores every edge sample),
+//                 ras_rows (1 lane / polygon row; short rows per lane, long rows
+//                 cooperatively across the warp).
+//   ras_shade     1 thread / pixel, streaming: key -> winner.  Small winners recompute
+//                 their row ends from the raw triangle (same 64-byte record that holds
+//                 the colour and normal the shader needs anyway); large winners read
+//                 their row record.  PixelShader in reference order, coalesced writes.
 #include <limits.h>
 
 #include "b2r_internal.h"
@@ -51,7 +60,7 @@ struct TriSetup {  // 24 words
     float vp[9];
     int minY, rows;
     unsigned rowBase, sampleBase;
-    int drawn, pad;
+    int drawn, tri;  // tri = index in the caller's triangle array (draw order)
 };
 
 struct EdgeSample {  // 5 words
@@ -82,47 +91,151 @@ __device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, 
     return p;
 }
 
-// ---- stage 1 ---------------------------------------------------------------
-__global__ void ras_setup_kernel(RasLaunch a, TriSetup* __restrict__ ts, uint2* __restrict__ counts,
-                                 unsigned* __restrict__ err) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.T) return;
-    uint2 cnt = make_uint2(0u, 0u);
-    TriSetup s;
-    s.drawn = 0;
-    s.rows = 0;
-    s.minY = 0;
-    s.rowBase = s.sampleBase = 0;
-    s.pad = 0;
-    bool culled = a.culled && a.culled[i];
-    if (!culled) {
+
+// ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
+constexpr int kSmallRows = 24;      // triangles up to this many polygon rows never leave the SM
+constexpr int kSmallThreads = 128;
+
+struct RasCounters {
+    unsigned nBig, bigRows, bigSamples, err;
+    unsigned long long pad;
+};
+
+__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri) {
+    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(0xFFFFFFFFu - tri);
+}
+
+// One edge of Interpolate (:615-637) reduced to the two chains the depth test depends on.
+struct EdgeStep {
+    int n, sgn;
+    float cx, cz, sx, sz;
+};
+__device__ __forceinline__ EdgeStep edge_begin(int xa, int ya, float za, int xb, int yb, float zb) {
+    EdgeStep e;
+    e.n = abs(ya - yb) + 1;                              // :712
+    e.sgn = (yb > ya) - (yb < ya);
+    const float div = (float)max(e.n - 1, 1);            // :622
+    e.sx = xdiv((float)(xb - xa), div);                  // Pixel operator- / fPixel operator/
+    e.sz = xdiv(xsub(zb, za), div);
+    e.cx = (float)xa;                                    // fPixel(Pixel&)
+    e.cz = za;
+    return e;
+}
+
+__global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
+                                                                   TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
+                                                                   int* __restrict__ bigSlot, RasCounters* __restrict__ ctr) {
+    // per-thread row ends, [row][field][thread] so that a warp's accesses never conflict
+    extern __shared__ int srow[];
+    int* const mine = srow + threadIdx.x;
+    auto LX = [&](int r) -> int& { return mine[(4 * r + 0) * kSmallThreads]; };
+    auto RX = [&](int r) -> int& { return mine[(4 * r + 1) * kSmallThreads]; };
+    auto LZ = [&](int r) -> float& { return reinterpret_cast<float*>(mine)[(4 * r + 2) * kSmallThreads]; };
+    auto RZ = [&](int r) -> float& { return reinterpret_cast<float*>(mine)[(4 * r + 3) * kSmallThreads]; };
+
+    const int i = blockIdx.x * kSmallThreads + threadIdx.x;
+    unsigned long long nTests = 0, nRows = 0, nDrawn = 0;
+    if (i < a.T && !(a.culled && a.culled[i])) {  // :470
         const float* t = reinterpret_cast<const float*>(a.raw + (size_t)i * a.stride);
+        RPixel v[3];
         int maxY = INT_MIN, minY = INT_MAX;
         bool bad = false;
+#pragma unroll
         for (int k = 0; k < 3; ++k) {
-            RPixel p = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);
-            s.vx[k] = p.x;
-            s.vy[k] = p.y;
-            s.vz[k] = p.zinv;
-            s.vp[3 * k] = p.p.x;
-            s.vp[3 * k + 1] = p.p.y;
-            s.vp[3 * k + 2] = p.p.z;
-            maxY = max(maxY, p.y);
-            minY = min(minY, p.y);
-            bad = bad || p.x <= -kCoordLimit || p.x >= kCoordLimit || p.y <= -kCoordLimit || p.y >= kCoordLimit;
+            v[k] = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);  // :760-761
+            maxY = max(maxY, v[k].y);
+            minY = min(minY, v[k].y);
+            bad = bad || v[k].x <= -kCoordLimit || v[k].x >= kCoordLimit || v[k].y <= -kCoordLimit || v[k].y >= kCoordLimit;
         }
-        if (bad || (maxY - minY + 1) > kMaxRowsPerTriangle) {
-            atomicExch(err, 1u);  // the reference would try to allocate/walk an absurd row count
-        } else {
-            s.drawn = 1;
+        const int rows = maxY - minY + 1;  // :682
+        if (bad || rows > kMaxRowsPerTriangle) {
+            atomicExch(&ctr->err, 1u);  // the reference would try to allocate/walk an absurd row count
+            bigSlot[i] = -1;
+        } else if (rows > kSmallRows) {
+            const unsigned samples = (unsigned)(abs(v[0].y - v[1].y) + abs(v[1].y - v[2].y) + abs(v[2].y - v[0].y) + 3);
+            const unsigned slot = atomicAdd(&ctr->nBig, 1u);
+            atomicAdd(&ctr->bigRows, (unsigned)rows);
+            atomicAdd(&ctr->bigSamples, samples);
+            TriSetup s;
+            for (int k = 0; k < 3; ++k) {
+                s.vx[k] = v[k].x;
+                s.vy[k] = v[k].y;
+                s.vz[k] = v[k].zinv;
+                s.vp[3 * k] = v[k].p.x;
+                s.vp[3 * k + 1] = v[k].p.y;
+                s.vp[3 * k + 2] = v[k].p.z;
+            }
             s.minY = minY;
-            s.rows = maxY - minY + 1;  // :682
-            cnt.x = (unsigned)s.rows;
-            cnt.y = (unsigned)(abs(s.vy[0] - s.vy[1]) + abs(s.vy[1] - s.vy[2]) + abs(s.vy[2] - s.vy[0]) + 3);  // :712
+            s.rows = rows;
+            s.rowBase = s.sampleBase = 0;
+            s.drawn = 1;
+            s.tri = i;
+            bigTs[slot] = s;
+            bigCounts[slot] = make_uint2((unsigned)rows, samples);
+            bigSlot[i] = (int)slot;
+            nDrawn = 1;
+            nRows = (unsigned long long)rows;
+        } else {
+            bigSlot[i] = -1;
+            nDrawn = 1;
+            nRows = (unsigned long long)rows;
+            for (int r = 0; r < rows; ++r) {  // :694-698
+                LX(r) = INT_MAX;
+                RX(r) = -INT_MAX;
+            }
+            // ComputePolygonRows: edges 0->1, 1->2, 2->0 in order, strict </> so the first edge to
+            // reach an extreme x keeps its attributes (:705-733)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int j = (e + 1) % 3;
+                EdgeStep st = edge_begin(v[e].x, v[e].y, v[e].zinv, v[j].x, v[j].y, v[j].zinv);
+                int r = v[e].y - minY;
+                for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
+                    const int x = f2i_x86(st.cx);
+                    if (x < LX(r)) {
+                        LX(r) = x;
+                        LZ(r) = st.cz;
+                    }
+                    if (x > RX(r)) {
+                        RX(r) = x;
+                        RZ(r) = st.cz;
+                    }
+                    st.cx = xadd(st.cx, st.sx);
+                    st.cz = xadd(st.cz, st.sz);
+                    r += st.sgn;
+                }
+            }
+            // DrawRows / DrawLineSDL / Bresenham with dy == 0 (:738-753, :592-612, :639-672)
+            const int r0 = max(0, a.y0 - minY), r1 = min(rows, a.y1 - minY);
+            for (int r = r0; r < r1; ++r) {
+                const int lx = LX(r), pixels = RX(r) - lx;       // :598
+                const float lz = LZ(r);
+                const float zstep = xdiv(xsub(RZ(r), lz), (float)pixels);  // :648
+                const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
+                unsigned long long* keyRow = keys + (size_t)(minY + r - a.y0) * (size_t)a.W;
+                for (int q = i0; q < i1; ++q) {
+                    const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
+                    if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
+                        atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i));
+                }
+                if (i1 > i0) nTests += (unsigned long long)(i1 - i0);
+            }
+        }
+    } else if (i < a.T) {
+        bigSlot[i] = -1;
+    }
+    if (a.stats) {
+        for (int off = 16; off > 0; off >>= 1) {
+            nTests += __shfl_xor_sync(0xffffffffu, nTests, off);
+            nRows += __shfl_xor_sync(0xffffffffu, nRows, off);
+            nDrawn += __shfl_xor_sync(0xffffffffu, nDrawn, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (nTests) atomicAdd(a.stats + B2R_STAT_RAS_DEPTH_TESTS, nTests);
+            if (nRows) atomicAdd(a.stats + B2R_STAT_RAS_ROWS, nRows);
+            if (nDrawn) atomicAdd(a.stats + B2R_STAT_RAS_TRIANGLES, nDrawn);
         }
     }
-    ts[i] = s;
-    counts[i] = cnt;
 }
 
 // ---- exclusive scan of uint2 (three small kernels) ---------------------------
@@ -190,7 +303,7 @@ __global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __r
 }
 
 // ---- stage 2: Interpolate (:615-637), one thread per (triangle, edge) --------
-__global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T, EdgeSample* __restrict__ samples,
+__global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* listed large triangles */, EdgeSample* __restrict__ samples,
                                  unsigned* __restrict__ rowOwner) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
     int i = gid / 3, e = gid - 3 * i;
@@ -258,10 +371,6 @@ __device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSampl
     return r;
 }
 
-__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri) {
-    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(0xFFFFFFFFu - tri);
-}
-
 // fragments i in [i0,i1) of one row; Bresenham with dy == 0 (:639-672): x = lx+1+i, zinv = lz + zstep*float(i)
 __device__ __forceinline__ void raster_span(unsigned long long* __restrict__ keyRow, int lx, float lz, float zstep,
                                             unsigned tri, int i0, int i1, int istride) {
@@ -273,6 +382,7 @@ __device__ __forceinline__ void raster_span(unsigned long long* __restrict__ key
 }
 
 constexpr int kShortRow = 8;
+
 
 __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restrict__ ts,
                                                        const EdgeSample* __restrict__ samples,
@@ -286,8 +396,8 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
     float lz = 0.f, zstep = 0.f;
     unsigned tri = 0;
     if (rid < nRows) {
-        tri = rowOwner[rid];
-        const TriSetup s = ts[tri];
+        const TriSetup s = ts[rowOwner[rid]];
+        tri = (unsigned)s.tri;
         y = s.minY + (int)(rid - s.rowBase);
         // DrawRows (:743): rows with y outside the screen are skipped; outside the band: another GPU's
         if (y >= y0 && y < y1) {
@@ -326,8 +436,54 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
     }
 }
 
-// ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------
-__global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ ts,
+// ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------------------------
+// Row ends of row y of a small triangle, recomputed from the raw record: VertexShader x3, then each edge
+// that spans the row is walked (all five chains of Interpolate) to its sample on that row.
+__device__ __forceinline__ RowRec small_triangle_row(const RasLaunch& a, const float* __restrict__ t, int y) {
+    RPixel v[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);
+    RowRec r;
+    r.lx = INT_MAX;    // :696
+    r.rx = -INT_MAX;   // :697
+    r.lz = r.rz = 0.f;
+    r.lp[0] = r.lp[1] = r.lp[2] = r.rp[0] = r.rp[1] = r.rp[2] = 0.f;
+    r.pad[0] = r.pad[1] = 0;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
+        const int j = (e + 1) % 3;
+        const int ya = v[e].y, yb = v[j].y;
+        if (y < min(ya, yb) || y > max(ya, yb)) continue;
+        const int n = abs(ya - yb) + 1;            // :712
+        const float div = (float)max(n - 1, 1);    // :622
+        const float sx = xdiv((float)(v[j].x - v[e].x), div);
+        const float sz = xdiv(xsub(v[j].zinv, v[e].zinv), div);
+        const V3 sp = xdivs3(xsub3(v[j].p, v[e].p), div);
+        float cx = (float)v[e].x, cz = v[e].zinv;
+        V3 cp = v[e].p;
+        const int steps = abs(y - ya);
+        for (int k = 0; k < steps; ++k) {          // :632-635
+            cx = xadd(cx, sx);
+            cz = xadd(cz, sz);
+            cp = xadd3(cp, sp);
+        }
+        const int x = f2i_x86(cx);
+        if (x < r.lx) {  // :718
+            r.lx = x;
+            r.lz = cz;
+            r.lp[0] = cp.x; r.lp[1] = cp.y; r.lp[2] = cp.z;
+        }
+        if (x > r.rx) {  // :726
+            r.rx = x;
+            r.rz = cz;
+            r.rp[0] = cp.x; r.rp[1] = cp.y; r.rp[2] = cp.z;
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
+                                                        const int* __restrict__ bigSlot,
                                                         const RowRec* __restrict__ rows,
                                                         const unsigned long long* __restrict__ keys) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,8 +498,15 @@ __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSe
         const DevFrame* __restrict__ f = a.frame;
         const unsigned tri = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
         winner = (int)tri;
-        const TriSetup* s = ts + tri;
-        const RowRec r = rows[s->rowBase + (unsigned)(y - s->minY)];
+        const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
+        const int slot = bigSlot[tri];
+        RowRec r;
+        if (slot >= 0) {
+            const TriSetup* s = bigTs + slot;
+            r = rows[s->rowBase + (unsigned)(y - s->minY)];
+        } else {
+            r = small_triangle_row(a, t, y);
+        }
         const int pixels = r.rx - r.lx;
         const float fi = (float)(x - r.lx - 1);
         const float fdx = (float)pixels;
@@ -351,7 +514,6 @@ __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSe
         const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
         const V3 pos3d = xadd3(lp, xscale3(xdivs3(xsub3(rp, lp), fdx), fi));                     // :649,668
         depth = zinv;  // == the key's high word
-        const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
         const V3 normal = mk3(t[9], t[10], t[11]), color = mk3(t[12], t[13], t[14]);
         const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
         V3 P = xdivs3(pos3d, zinv);        // :557
@@ -384,23 +546,6 @@ __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSe
     }
     if (a.focal) a.focal[idx] = focal;
     if (a.winner) a.winner[idx] = winner;
-}
-
-__global__ void ras_count_kernel(const TriSetup* __restrict__ ts, int T, unsigned long long* __restrict__ stats) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long d = 0, r = 0;
-    if (i < T && ts[i].drawn) {
-        d = 1;
-        r = (unsigned long long)ts[i].rows;
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        d += __shfl_xor_sync(0xffffffffu, d, off);
-        r += __shfl_xor_sync(0xffffffffu, r, off);
-    }
-    if ((threadIdx.x & 31) == 0 && d) {
-        atomicAdd(stats + B2R_STAT_RAS_TRIANGLES, d);
-        atomicAdd(stats + B2R_STAT_RAS_ROWS, r);
-    }
 }
 
 // ---- culling block of Update() (:385-447) ------------------------------------
@@ -466,49 +611,54 @@ cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s) {
 }
 
 // Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
+
+// Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
 cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     const int T = a.T;
     const int bandH = a.y1 - a.y0;
     cudaError_t e;
-    // scratch layout: [counts uint2 x T][excl uint2 x T][blockSums uint2 x nb][totals uint2][err u32]
-    const int nb = (T + kScanBlock - 1) / kScanBlock;
-    const size_t offCounts = 0, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
+    // scratch: [counters 64 B][bigCounts uint2 x T][excl uint2 x T][blockSums][totals]; bigSlot int x T separately
+    const int nbMax = (T + kScanBlock - 1) / kScanBlock + 1;
+    const size_t offCtr = 0, offCounts = 256, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
                  offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
-                 offTotals = align_up(offSums + sizeof(uint2) * (size_t)(nb + 1), 256), offErr = offTotals + 64,
-                 scratchBytes = offErr + 64;
+                 offTotals = align_up(offSums + sizeof(uint2) * (size_t)nbMax, 256), scratchBytes = offTotals + 256;
     if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
-    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1))) != cudaSuccess) return e;
+    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int) * (size_t)(T + 1) + 512)) != cudaSuccess) return e;
     if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
     unsigned char* sc = c->rasScratch.as<unsigned char>();
+    RasCounters* ctr = reinterpret_cast<RasCounters*>(sc + offCtr);
     uint2* counts = reinterpret_cast<uint2*>(sc + offCounts);
     uint2* excl = reinterpret_cast<uint2*>(sc + offExcl);
     uint2* sums = reinterpret_cast<uint2*>(sc + offSums);
     uint2* totals = reinterpret_cast<uint2*>(sc + offTotals);
-    unsigned* err = reinterpret_cast<unsigned*>(sc + offErr);
-    TriSetup* ts = c->rasTri.as<TriSetup>();
+    int* bigSlot = c->rasTri.as<int>();
+    TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int) * (size_t)(T + 1), 256));
     unsigned long long* keys = c->rasKeys.as<unsigned long long>();
 
-    if ((e = cudaMemsetAsync(totals, 0, 128, s)) != cudaSuccess) return e;  // totals + err
+    if ((e = cudaMemsetAsync(ctr, 0, sizeof(RasCounters), s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)bandH * a.W, s)) != cudaSuccess) return e;  // depthBuffer = 0 (:188)
-    uint2 hostTotals = make_uint2(0u, 0u);
-    unsigned hostErr = 0;
+    RasCounters host{};
+    const RowRec* rowsPtr = nullptr;
     if (T > 0) {
-        ras_setup_kernel<<<(T + 255) / 256, 256, 0, s>>>(a, ts, counts, err);
-        scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, T);
-        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
-        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, T);
-        c->launches += 4;
+        const size_t smem = sizeof(int) * 4 * kSmallRows * kSmallThreads;
+        static bool attrSet = false;
+        if (!attrSet) {
+            if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+            attrSet = true;
+        }
+        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, bigSlot, ctr);
+        c->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        // buffer sizes depend on the projected geometry: read the two totals back (8 bytes)
-        if ((e = cudaMemcpyAsync(c->pinned, totals, sizeof(uint2), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync((char*)c->pinned + 16, err, sizeof(unsigned), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        // how many large triangles / rows / edge samples: 16 bytes back to size the big path
+        if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-        hostTotals = *reinterpret_cast<uint2*>(c->pinned);
-        hostErr = *reinterpret_cast<unsigned*>((char*)c->pinned + 16);
-        if (hostErr) return cudaErrorInvalidValue;
+        host = *reinterpret_cast<RasCounters*>(c->pinned);
+        if (host.err) return cudaErrorInvalidValue;
     }
-    const unsigned nRows = hostTotals.x, nSamples = hostTotals.y;
-    if (nRows > 0) {
+    if (host.nBig > 0) {
+        const int nBig = (int)host.nBig;
+        const unsigned nRows = host.bigRows, nSamples = host.bigSamples;
+        const int nb = (nBig + kScanBlock - 1) / kScanBlock;
         if ((e = c->rasRows.reserve(sizeof(RowRec) * (size_t)nRows + sizeof(unsigned) * (size_t)nRows +
                                     sizeof(EdgeSample) * (size_t)nSamples + 1024)) != cudaSuccess)
             return e;
@@ -517,19 +667,18 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
         unsigned* owner = reinterpret_cast<unsigned*>(rb + align_up(sizeof(RowRec) * (size_t)nRows, 256));
         EdgeSample* samples = reinterpret_cast<EdgeSample*>(reinterpret_cast<unsigned char*>(owner) +
                                                             align_up(sizeof(unsigned) * (size_t)nRows, 256));
-        ras_edges_kernel<<<(3 * T + 127) / 128, 128, 0, s>>>(ts, T, samples, owner);
-        ras_rows_kernel<<<(nRows + 255) / 256, 256, 0, s>>>(ts, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1,
-                                                           a.stats);
-        c->launches += 2;
-        if (a.stats) {
-            ras_count_kernel<<<(T + 255) / 256, 256, 0, s>>>(ts, T, a.stats);
-            c->launches++;
-        }
+        rowsPtr = rows;
+        scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, nBig);
+        scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
+        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
+        ras_edges_kernel<<<(3 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, samples, owner);
+        ras_rows_kernel<<<(nRows + 255) / 256, 256, 0, s>>>(ts, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
+        c->launches += 5;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     {
         dim3 grid((a.W + 255) / 256, bandH);
-        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, c->rasRows.as<RowRec>(), keys);
+        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, bigSlot, rowsPtr, keys);
         c->launches++;
     }
     return cudaGetLastError();
