@@ -48,6 +48,15 @@ __device__ __forceinline__ int f2i_x86(float f) {
     return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
 }
 
+// IEEE a/b for the edge-step set-up, where a is very often exactly 0 (axis-aligned edges of a regular mesh).
+// __fdiv_rn's fast path bails out to a ~100-instruction routine for a zero numerator, and a warp pays for it
+// if any lane does; 0/b is +-0 with the XOR of the signs for every finite non-zero or infinite b.
+__device__ __forceinline__ float xdiv_step(float a, float b) {
+    if (a == 0.0f && b != 0.0f && b == b)
+        return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000);
+    return xdiv(a, b);
+}
+
 struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
     int x, y;
     float zinv;
@@ -101,6 +110,15 @@ struct RasCounters {
     unsigned long long pad;
 };
 
+// Projected vertices of a small triangle (VertexShader output, :532-546), kept for the shade pass: 64 bytes.
+// pos3d.z is omitted: it is pos.z/pos.z == 1.0f exactly for every triangle that passes the coordinate
+// limits, and Interpolate's z step is then (1-1)/n == 0, so the chain stays 1.0f.
+struct VsRec {
+    int x[3], y[3];
+    float z[3], px[3], py[3];
+    int pad;
+};
+
 __device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri) {
     return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(0xFFFFFFFFu - tri);
 }
@@ -115,8 +133,8 @@ __device__ __forceinline__ EdgeStep edge_begin(int xa, int ya, float za, int xb,
     e.n = abs(ya - yb) + 1;                              // :712
     e.sgn = (yb > ya) - (yb < ya);
     const float div = (float)max(e.n - 1, 1);            // :622
-    e.sx = xdiv((float)(xb - xa), div);                  // Pixel operator- / fPixel operator/
-    e.sz = xdiv(xsub(zb, za), div);
+    e.sx = xdiv_step((float)(xb - xa), div);             // Pixel operator- / fPixel operator/
+    e.sz = xdiv_step(xsub(zb, za), div);
     e.cx = (float)xa;                                    // fPixel(Pixel&)
     e.cz = za;
     return e;
@@ -124,7 +142,8 @@ __device__ __forceinline__ EdgeStep edge_begin(int xa, int ya, float za, int xb,
 
 __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
                                                                    TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
-                                                                   int* __restrict__ bigSlot, RasCounters* __restrict__ ctr) {
+                                                                   int* __restrict__ bigSlot, VsRec* __restrict__ vsOut,
+                                                                   RasCounters* __restrict__ ctr) {
     // per-thread row ends, [row][field][thread] so that a warp's accesses never conflict
     extern __shared__ int srow[];
     int* const mine = srow + threadIdx.x;
@@ -179,6 +198,13 @@ __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, u
             bigSlot[i] = -1;
             nDrawn = 1;
             nRows = (unsigned long long)rows;
+            {
+                float4* o = reinterpret_cast<float4*>(vsOut + i);
+                o[0] = make_float4(__int_as_float(v[0].x), __int_as_float(v[1].x), __int_as_float(v[2].x), __int_as_float(v[0].y));
+                o[1] = make_float4(__int_as_float(v[1].y), __int_as_float(v[2].y), v[0].zinv, v[1].zinv);
+                o[2] = make_float4(v[2].zinv, v[0].p.x, v[1].p.x, v[2].p.x);
+                o[3] = make_float4(v[0].p.y, v[1].p.y, v[2].p.y, 0.f);
+            }
             for (int r = 0; r < rows; ++r) {  // :694-698
                 LX(r) = INT_MAX;
                 RX(r) = -INT_MAX;
@@ -318,11 +344,12 @@ __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* liste
     for (int k = 0; k < e; ++k) off += (unsigned)(abs(s.vy[k] - s.vy[(k + 1) % 3]) + 1);
     const float div = (float)max(n - 1, 1);  // :622
     // Pixel operator- (TestModel.h:82-85) then fPixel operator/ (:124-127)
-    const float sx = xdiv((float)(s.vx[j] - s.vx[e]), div);
-    const float sz = xdiv(xsub(s.vz[j], s.vz[e]), div);
+    const float sx = xdiv_step((float)(s.vx[j] - s.vx[e]), div);
+    const float sz = xdiv_step(xsub(s.vz[j], s.vz[e]), div);
     const V3 a3 = mk3(s.vp[3 * e], s.vp[3 * e + 1], s.vp[3 * e + 2]);
     const V3 b3 = mk3(s.vp[3 * j], s.vp[3 * j + 1], s.vp[3 * j + 2]);
-    const V3 sp = xdivs3(xsub3(b3, a3), div);
+    const V3 d3 = xsub3(b3, a3);
+    const V3 sp = mk3(xdiv_step(d3.x, div), xdiv_step(d3.y, div), xdiv_step(d3.z, div));
     float cx = (float)s.vx[e], cz = s.vz[e];  // fPixel(Pixel&)
     V3 cp = a3;
     EdgeSample* out = samples + off;
@@ -437,53 +464,57 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
 }
 
 // ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------------------------
-// Row ends of row y of a small triangle, recomputed from the raw record: VertexShader x3, then each edge
-// that spans the row is walked (all five chains of Interpolate) to its sample on that row.
-__device__ __forceinline__ RowRec small_triangle_row(const RasLaunch& a, const float* __restrict__ t, int y) {
-    RPixel v[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v[k] = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);
+// Row ends of row y of a small triangle from its projected vertices: each edge that spans the row is
+// walked (the x, zinv and pos3d.xy chains of Interpolate) to its sample on that row.
+__device__ __forceinline__ RowRec small_triangle_row(const VsRec* __restrict__ rec, int y) {
+    const float4* q = reinterpret_cast<const float4*>(rec);
+    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
+    const int vx[3] = {__float_as_int(q0.x), __float_as_int(q0.y), __float_as_int(q0.z)};
+    const int vy[3] = {__float_as_int(q0.w), __float_as_int(q1.x), __float_as_int(q1.y)};
+    const float vz[3] = {q1.z, q1.w, q2.x};
+    const float px[3] = {q2.y, q2.z, q2.w}, py[3] = {q3.x, q3.y, q3.z};
     RowRec r;
     r.lx = INT_MAX;    // :696
     r.rx = -INT_MAX;   // :697
     r.lz = r.rz = 0.f;
-    r.lp[0] = r.lp[1] = r.lp[2] = r.rp[0] = r.rp[1] = r.rp[2] = 0.f;
+    r.lp[0] = r.lp[1] = r.rp[0] = r.rp[1] = 0.f;
+    r.lp[2] = r.rp[2] = 1.0f;
     r.pad[0] = r.pad[1] = 0;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
         const int j = (e + 1) % 3;
-        const int ya = v[e].y, yb = v[j].y;
+        const int ya = vy[e], yb = vy[j];
         if (y < min(ya, yb) || y > max(ya, yb)) continue;
         const int n = abs(ya - yb) + 1;            // :712
         const float div = (float)max(n - 1, 1);    // :622
-        const float sx = xdiv((float)(v[j].x - v[e].x), div);
-        const float sz = xdiv(xsub(v[j].zinv, v[e].zinv), div);
-        const V3 sp = xdivs3(xsub3(v[j].p, v[e].p), div);
-        float cx = (float)v[e].x, cz = v[e].zinv;
-        V3 cp = v[e].p;
+        const float sx = xdiv_step((float)(vx[j] - vx[e]), div);
+        const float sz = xdiv_step(xsub(vz[j], vz[e]), div);
+        const float spx = xdiv_step(xsub(px[j], px[e]), div), spy = xdiv_step(xsub(py[j], py[e]), div);
+        float cx = (float)vx[e], cz = vz[e], cpx = px[e], cpy = py[e];
         const int steps = abs(y - ya);
         for (int k = 0; k < steps; ++k) {          // :632-635
             cx = xadd(cx, sx);
             cz = xadd(cz, sz);
-            cp = xadd3(cp, sp);
+            cpx = xadd(cpx, spx);
+            cpy = xadd(cpy, spy);
         }
         const int x = f2i_x86(cx);
         if (x < r.lx) {  // :718
             r.lx = x;
             r.lz = cz;
-            r.lp[0] = cp.x; r.lp[1] = cp.y; r.lp[2] = cp.z;
+            r.lp[0] = cpx; r.lp[1] = cpy;
         }
         if (x > r.rx) {  // :726
             r.rx = x;
             r.rz = cz;
-            r.rp[0] = cp.x; r.rp[1] = cp.y; r.rp[2] = cp.z;
+            r.rp[0] = cpx; r.rp[1] = cpy;
         }
     }
     return r;
 }
 
 __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
-                                                        const int* __restrict__ bigSlot,
+                                                        const int* __restrict__ bigSlot, const VsRec* __restrict__ vs,
                                                         const RowRec* __restrict__ rows,
                                                         const unsigned long long* __restrict__ keys) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,7 +536,7 @@ __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSe
             const TriSetup* s = bigTs + slot;
             r = rows[s->rowBase + (unsigned)(y - s->minY)];
         } else {
-            r = small_triangle_row(a, t, y);
+            r = small_triangle_row(vs + tri, y);
         }
         const int pixels = r.rx - r.lx;
         const float fi = (float)(x - r.lx - 1);
@@ -623,7 +654,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
                  offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
                  offTotals = align_up(offSums + sizeof(uint2) * (size_t)nbMax, 256), scratchBytes = offTotals + 256;
     if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
-    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int) * (size_t)(T + 1) + 512)) != cudaSuccess) return e;
+    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int) * (size_t)(T + 1) + sizeof(VsRec) * (size_t)(T + 1) + 1024)) != cudaSuccess) return e;
     if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
     unsigned char* sc = c->rasScratch.as<unsigned char>();
     RasCounters* ctr = reinterpret_cast<RasCounters*>(sc + offCtr);
@@ -632,7 +663,8 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     uint2* sums = reinterpret_cast<uint2*>(sc + offSums);
     uint2* totals = reinterpret_cast<uint2*>(sc + offTotals);
     int* bigSlot = c->rasTri.as<int>();
-    TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int) * (size_t)(T + 1), 256));
+    VsRec* vs = reinterpret_cast<VsRec*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int) * (size_t)(T + 1), 256));
+    TriSetup* ts = reinterpret_cast<TriSetup*>(reinterpret_cast<unsigned char*>(vs) + align_up(sizeof(VsRec) * (size_t)(T + 1), 256));
     unsigned long long* keys = c->rasKeys.as<unsigned long long>();
 
     if ((e = cudaMemsetAsync(ctr, 0, sizeof(RasCounters), s)) != cudaSuccess) return e;
@@ -646,7 +678,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
             if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
             attrSet = true;
         }
-        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, bigSlot, ctr);
+        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, bigSlot, vs, ctr);
         c->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         // how many large triangles / rows / edge samples: 16 bytes back to size the big path
@@ -678,7 +710,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     }
     {
         dim3 grid((a.W + 255) / 256, bandH);
-        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, bigSlot, rowsPtr, keys);
+        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, bigSlot, vs, rowsPtr, keys);
         c->launches++;
     }
     return cudaGetLastError();
