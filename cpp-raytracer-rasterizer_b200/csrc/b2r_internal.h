@@ -139,6 +139,8 @@ struct Ctx {
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch;
+    size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
+    void* rasKeysCleanPtr = nullptr;
     // pinned staging for host-pointer entry points
     void* pinned = nullptr;
     size_t pinnedCap = 0;

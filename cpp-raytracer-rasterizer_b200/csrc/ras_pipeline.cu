@@ -20,7 +20,7 @@
 // depth test, so it is replayed step by step, never re-associated.
 //
 // Pipeline (v2):
-//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 24 rows
+//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 16 rows
 //                 (the 1M-triangle regime) are finished here: the three edge walks
 //                 (x and zinv chains only) update per-row left/right ends kept in
 //                 shared memory, then every on-screen fragment goes to the key
@@ -102,7 +102,7 @@ __device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, 
 
 
 // ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
-constexpr int kSmallRows = 24;      // triangles up to this many polygon rows never leave the SM
+constexpr int kSmallRows = 16;      // triangles up to this many polygon rows never leave the SM
 constexpr int kSmallThreads = 128;
 
 struct RasCounters {
@@ -516,12 +516,14 @@ __device__ __forceinline__ RowRec small_triangle_row(const VsRec* __restrict__ r
 __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
                                                         const int* __restrict__ bigSlot, const VsRec* __restrict__ vs,
                                                         const RowRec* __restrict__ rows,
-                                                        const unsigned long long* __restrict__ keys) {
+                                                        unsigned long long* __restrict__ keys) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = a.y0 + blockIdx.y;
     if (x >= a.W || y >= a.y1) return;
     const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
-    const unsigned long long key = keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x];
+    const size_t kidx = (size_t)(y - a.y0) * (size_t)a.W + (size_t)x;
+    const unsigned long long key = keys[kidx];
+    if (key != 0ull) keys[kidx] = 0ull;  // depthBuffer = 0 (:188) for the next frame, in the same pass
     float depth = 0.f, focal = 0.f;
     V3 colour = mk3(0.f, 0.f, 0.f);
     int winner = -1;
@@ -561,7 +563,7 @@ __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSe
             const float A = sphere_area(rr);                   // :576
             const V3 lc = mk3(f->lightColor[k][0], f->lightColor[k][1], f->lightColor[k][2]);  // :577
             const V3 rDir = xscale3(dl, xdiv(1.0f, rr));       // :578
-            const V3 B = xdivs3(lc, A);                        // :580
+            const V3 B = xdivs3_shared(lc, A);                 // :580
             const V3 D = xscale3(B, std_max(xdot3(rDir, normal), 0.0f));  // :582 (normal not re-normalised)
             result = xadd3(result, D);
         }
@@ -668,7 +670,13 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     unsigned long long* keys = c->rasKeys.as<unsigned long long>();
 
     if ((e = cudaMemsetAsync(ctr, 0, sizeof(RasCounters), s)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)bandH * a.W, s)) != cudaSuccess) return e;  // depthBuffer = 0 (:188)
+    // depthBuffer = 0 (:188): the shade pass of the previous frame leaves the key buffer cleared; clear it here
+    // only when the buffer is new or was last used for a different band size
+    const size_t keyBytes = sizeof(unsigned long long) * (size_t)bandH * a.W;
+    if (c->rasKeysClean != keyBytes || c->rasKeysCleanPtr != (void*)keys) {
+        if ((e = cudaMemsetAsync(keys, 0, keyBytes, s)) != cudaSuccess) return e;
+    }
+    c->rasKeysClean = 0;
     RasCounters host{};
     const RowRec* rowsPtr = nullptr;
     if (T > 0) {
@@ -713,7 +721,12 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
         ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, bigSlot, vs, rowsPtr, keys);
         c->launches++;
     }
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        c->rasKeysClean = keyBytes;
+        c->rasKeysCleanPtr = keys;
+    }
+    return e;
 }
 
 }  // namespace b2r

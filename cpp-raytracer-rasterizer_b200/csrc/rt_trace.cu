@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_c
                             V3 D = mk3(0.f, 0.f, 0.f);
                             if (any) {
                                 const float A = sphere_area(r);      // :295
-                                const V3 B = xdivs3(P, A);           // :301
+                                const V3 B = xdivs3_shared(P, A);    // :301
                                 D = xscale3(B, std_max(xdot3(rDir, nDir), 0.0f));  // :304
                                 if constexpr (STATS) cnt.shadow++;
                             }
