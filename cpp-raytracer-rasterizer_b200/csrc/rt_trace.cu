@@ -337,7 +337,7 @@ __device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_s
 // The kernel.  TILECULL = false keeps only the per-ray filter (every ray looks at every triangle).
 // ---------------------------------------------------------------------------
 template <bool TILECULL, bool FILTER, bool STATS>
-__global__ void __launch_bounds__(kThreads) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
+__global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
