@@ -94,6 +94,8 @@ SYMBOLS = [
     "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_launch_count", "b2r_get_stats",
     "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_scene_cornell_box",
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
+    "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
+    "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async",
 ]
 
 _lib = None
@@ -135,6 +137,12 @@ def load_library():
     lib.b2r_rt_draw_device_async.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.b2r_ras_draw_device_async.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.b2r_resolve_surface_device_async.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.b2r_shared_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
+    lib.b2r_shared_free.argtypes = [vp, vp]
+    lib.b2r_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.b2r_shared_close.argtypes = [vp, vp]
+    lib.b2r_copy_device_async.argtypes = [vp, vp, vp, C.c_size_t]
+    lib.b2r_resolve_surface_multi_device_async.argtypes = [vp, i32, i32, vp, vp, C.POINTER(vp), i32]
     lib.b2r_launch_count.argtypes = [vp]
     lib.b2r_launch_count.restype = C.c_ulonglong
     lib.b2r_get_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -292,6 +300,34 @@ class Context:
     def resolve_surface_device_async(self, y0, y1, d_colours, d_focal, d_surface):
         self._chk(self.lib.b2r_resolve_surface_device_async(self.handle, y0, y1, C.c_void_p(d_colours),
                                                             C.c_void_p(d_focal), C.c_void_p(d_surface)))
+
+    # fused band exchange (one process per GPU, peer-mapped surfaces) -----------------------------
+    def shared_alloc(self, nbytes):
+        """cudaMalloc on this GPU; returns (device address, 64-byte IPC handle)."""
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64)()
+        self._chk(self.lib.b2r_shared_alloc(self.handle, nbytes, C.byref(p), h))
+        return p.value, bytes(h)
+
+    def shared_free(self, addr):
+        self._chk(self.lib.b2r_shared_free(self.handle, C.c_void_p(addr)))
+
+    def shared_open(self, handle_bytes):
+        p = C.c_void_p()
+        h = (C.c_ubyte * 64).from_buffer_copy(handle_bytes)
+        self._chk(self.lib.b2r_shared_open(self.handle, h, C.byref(p)))
+        return p.value
+
+    def shared_close(self, addr):
+        self._chk(self.lib.b2r_shared_close(self.handle, C.c_void_p(addr)))
+
+    def copy_device_async(self, d_dst, d_src, nbytes):
+        self._chk(self.lib.b2r_copy_device_async(self.handle, C.c_void_p(d_dst), C.c_void_p(d_src), nbytes))
+
+    def resolve_surface_multi_device_async(self, y0, y1, d_colours, d_focal, d_surfaces):
+        arr = (C.c_void_p * len(d_surfaces))(*d_surfaces)
+        self._chk(self.lib.b2r_resolve_surface_multi_device_async(self.handle, y0, y1, C.c_void_p(d_colours),
+                                                                  C.c_void_p(d_focal), arr, len(d_surfaces)))
 
     def measure_fp32_peak(self):
         t, s = C.c_double(), C.c_double()

@@ -491,6 +491,72 @@ int b2r_resolve_surface_device_async(b2r_ctx* ctx, int y0, int y1, const float* 
     return B2R_OK;
 }
 
+int b2r_resolve_surface_multi_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_col, const float* d_foc,
+                                           uint32_t* const* d_surfaces, int n) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (y0 < 0 || y1 > c->H || y0 > y1 || !d_col || !d_surfaces || n < 1 || n > B2R_MAX_PEERS)
+        return fail(c, B2R_E_INVALID, "resolve_multi: bad arguments (1..8 destination surfaces)");
+    for (int i = 0; i < n; ++i)
+        if (!d_surfaces[i]) return fail(c, B2R_E_INVALID, "resolve_multi: null destination");
+    if (c->params.dofEnabled && !d_foc) return fail(c, B2R_E_INVALID, "resolve: depth of field needs focalDistances");
+    CU(launch_resolve_surface_multi(c, y0, y1, d_col, d_foc, d_surfaces, n, c->stream), "resolve_surface_kernel");
+    return B2R_OK;
+}
+
+// ---- inter-process shared device buffers (CUDA IPC) for the fused band exchange -----------------
+int b2r_shared_alloc(b2r_ctx* ctx, size_t bytes, void** d_ptr, void* handle_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!d_ptr || !handle_out || bytes == 0) return fail(c, B2R_E_INVALID, "shared_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B2R_IPC_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes), "cudaMalloc (shared)");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(c, e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle_out, &h, sizeof h);
+    *d_ptr = p;
+    return B2R_OK;
+}
+
+int b2r_shared_free(b2r_ctx* ctx, void* d_ptr) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (d_ptr) CU(cudaFree(d_ptr), "cudaFree (shared)");
+    return B2R_OK;
+}
+
+int b2r_shared_open(b2r_ctx* ctx, const void* handle, void** d_ptr) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!handle || !d_ptr) return fail(c, B2R_E_INVALID, "shared_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    *d_ptr = p;
+    return B2R_OK;
+}
+
+int b2r_copy_device_async(b2r_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!d_dst || !d_src) return fail(c, B2R_E_INVALID, "copy_device: null pointer");
+    if (bytes) CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream), "cudaMemcpyAsync D2D");
+    return B2R_OK;
+}
+
+int b2r_shared_close(b2r_ctx* ctx, void* d_ptr) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr), "cudaIpcCloseMemHandle");
+    return B2R_OK;
+}
+
 int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;

@@ -86,6 +86,8 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s);
 cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s);
 cudaError_t launch_resolve_surface(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
                                    uint32_t* d_surface, cudaStream_t s);
+cudaError_t launch_resolve_surface_multi(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
+                                         uint32_t* const* d_surfaces, int n, cudaStream_t s);
 cudaError_t launch_surface_to_bgr8(Ctx* c, const uint32_t* d_surface, uint8_t* d_bgr, cudaStream_t s);
 cudaError_t run_fp32_peak(Ctx* c, double* tflops, double* seconds);
 

@@ -20,10 +20,16 @@ __device__ __forceinline__ uint32_t quantise(float c) {
 // Out-of-range policy for the DOF window (the reference reads without bounds checks,
 // raytracer.cpp:637): the flattened index is used as-is inside [0, W*H) (columns wrap into
 // the neighbouring row exactly like the reference) and contributes 0 outside the array.
+// Destinations of one resolve: the local surface and/or peer-mapped surfaces of other GPUs (stores go over
+// NVLink), which fuses the framebuffer-band exchange of a single-frame multi-GPU split into this kernel.
+struct SurfDst {
+    uint32_t* p[B2R_MAX_PEERS];
+    int n;
+};
+
 __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __restrict__ colours,
                                                               const float* __restrict__ focal, int W, int H,
-                                                              int y0, int dof, int K,
-                                                              uint32_t* __restrict__ surface) {
+                                                              int y0, int dof, int K, const SurfDst dst) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = y0 + blockIdx.y;
     if (x >= W) return;
@@ -55,17 +61,28 @@ __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __res
         }
         out = (quantise(fr) << 16) | (quantise(fg) << 8) | quantise(fb);    // SDL_MapRGB on XRGB8888
     }
-    surface[(size_t)y * W + x] = out;
+    const size_t o = (size_t)y * W + x;
+#pragma unroll
+    for (int d = 0; d < B2R_MAX_PEERS; ++d)
+        if (d < dst.n) dst.p[d][o] = out;
+}
+
+cudaError_t launch_resolve_surface_multi(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
+                                         uint32_t* const* d_surfaces, int n, cudaStream_t s) {
+    if (y1 <= y0 || n <= 0) return cudaSuccess;
+    SurfDst dst;
+    dst.n = n;
+    for (int d = 0; d < B2R_MAX_PEERS; ++d) dst.p[d] = d < n ? d_surfaces[d] : nullptr;
+    dim3 grid((c->W + 255) / 256, y1 - y0);
+    resolve_surface_kernel<<<grid, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0,
+                                                c->params.dofEnabled ? 1 : 0, c->params.dofKernelSize, dst);
+    c->launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_surface(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
                                    uint32_t* d_surface, cudaStream_t s) {
-    if (y1 <= y0) return cudaSuccess;
-    dim3 grid((c->W + 255) / 256, y1 - y0);
-    resolve_surface_kernel<<<grid, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0,
-                                                c->params.dofEnabled ? 1 : 0, c->params.dofKernelSize, d_surface);
-    c->launches++;
-    return cudaGetLastError();
+    return launch_resolve_surface_multi(c, y0, y1, d_colours, d_focal, &d_surface, 1, s);
 }
 
 // XRGB surface -> bottom-up BGR rows padded to 4 bytes.

@@ -192,6 +192,26 @@ int b2r_set_option(b2r_ctx* ctx, int option, int value);
 /* Device FP32 FFMA throughput microbenchmark (TFLOP/s), the raytracer's roofline denominator. */
 int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds);
 
+/* ---- single-frame split across GPUs: resolve fused with the band exchange ---- */
+/* One process per GPU.  Each rank renders its row band (y0,y1 of the draw calls) and resolves it
+ * DIRECTLY into the surface buffers of its peers with stores over NVLink (peer-mapped pointers), so
+ * the gather of framebuffer bands needs no separate collective -- only a barrier afterwards.
+ *   b2r_shared_alloc        cudaMalloc on this context's GPU + a 64-byte inter-process handle
+ *   b2r_shared_open/close   map a peer's allocation into this process (cudaIpcOpenMemHandle)
+ *   b2r_resolve_surface_multi_device_async
+ *                           rows [y0,y1): one kernel, every pixel written to each of n (<= 8)
+ *                           destination surfaces (local or peer-mapped) */
+#define B2R_IPC_HANDLE_BYTES 64
+#define B2R_MAX_PEERS 8
+int b2r_shared_alloc(b2r_ctx* ctx, size_t bytes, void** d_ptr, void* handle_out /* 64 bytes */);
+int b2r_shared_free(b2r_ctx* ctx, void* d_ptr);
+int b2r_shared_open(b2r_ctx* ctx, const void* handle /* 64 bytes */, void** d_ptr);
+int b2r_shared_close(b2r_ctx* ctx, void* d_ptr);
+/* Device-to-device copy on the context's stream (e.g. out of a shared buffer into caller-owned memory). */
+int b2r_copy_device_async(b2r_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int b2r_resolve_surface_multi_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_pixelColours,
+                                           const float* d_focalDistances, uint32_t* const* d_surfaces, int n);
+
 /* ---- host-side scene helpers (no GPU involved) ---------------------------- */
 /* LoadTestModel (raytracer TestModel.h:51-192 == rasteriser TestModel.h:151-292): the 30-triangle
  * Cornell box, written as reference Triangle records of the given stride (60 or 64).  Returns the

@@ -1,0 +1,102 @@
+"""Worker for tests/test_multigpu.py (run under torch.distributed.run, one rank per GPU).
+
+Single-frame split: every rank renders its row band of the same frame, resolves it with ONE kernel straight
+into every rank's surface (peer-mapped buffers, stores over NVLink), barrier, and every rank compares the
+assembled frame with a frame it rendered alone.  Also checks the NCCL all-gather variant and the
+frame-partitioned orbit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = g.load_package()
+    par = pkg.parallel
+    w, h = 640, 360
+    ctx = pkg.Context(w, h, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_triangles(pkg.cornell_box())
+    fp = pkg.default_frame_params(0, w, h)
+    fp.aaEnabled, fp.aaSamples = 1, 2
+    ctx.set_frame(fp)
+    col = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    # reference: this rank renders the whole frame alone
+    ref_surf = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    ctx.rt_draw_device_async(0, h, col.data_ptr())
+    ctx.resolve_surface_device_async(0, h, col.data_ptr(), 0, ref_surf.data_ptr())
+    ctx.synchronize()
+
+    # --- fused exchange: shared surfaces, one per rank
+    mine, handle = ctx.shared_alloc(w * h * 4)
+    handles = [None] * world
+    dist.all_gather_object(handles, handle)
+    ptrs = [mine if r == rank else ctx.shared_open(handles[r]) for r in range(world)]
+    y0, y1 = par.row_band(rank, world, h)
+    col.zero_()
+    ctx.rt_draw_device_async(y0, y1, col.data_ptr())
+    ctx.resolve_surface_multi_device_async(y0, y1, col.data_ptr(), 0, ptrs)
+    ctx.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    # read the shared buffer back through torch: device-to-device copy from the raw pointer
+    tmp = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    ctx.copy_device_async(tmp.data_ptr(), mine, w * h * 4)
+    ctx.synchronize()
+    assert torch.equal(tmp, ref_surf), f"rank {rank}: fused band exchange differs from the single-GPU frame"
+
+    # --- NCCL variant (parallel.gather_bands)
+    surf = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    ctx.resolve_surface_device_async(y0, y1, col.data_ptr(), 0, surf.data_ptr())
+    ctx.synchronize()
+    par.gather_bands(surf, rank, world)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(surf, ref_surf), f"rank {rank}: NCCL band gather differs"
+
+    # --- frame partition of an orbit: no collective on the data path; checksum of checksums over all frames
+    nframes = 8
+    sums = torch.zeros(nframes, dtype=torch.int64, device=dev)
+    for fidx in par.frames_for_rank(rank, world, nframes):
+        pos, rot = pkg.orbit_camera(fidx, nframes)
+        fp.set_camera(pos, rot, h / 2)
+        ctx.set_frame(fp)
+        ctx.rt_draw_device_async(0, h, col.data_ptr())
+        ctx.resolve_surface_device_async(0, h, col.data_ptr(), 0, surf.data_ptr())
+        ctx.synchronize()
+        sums[fidx] = surf.to(torch.int64).sum()
+    dist.all_reduce(sums)
+    if rank == 0:
+        alone = []
+        for fidx in range(nframes):
+            pos, rot = pkg.orbit_camera(fidx, nframes)
+            fp.set_camera(pos, rot, h / 2)
+            ctx.set_frame(fp)
+            ctx.rt_draw_device_async(0, h, col.data_ptr())
+            ctx.resolve_surface_device_async(0, h, col.data_ptr(), 0, surf.data_ptr())
+            ctx.synchronize()
+            alone.append(int(surf.to(torch.int64).sum()))
+        assert alone == sums.tolist(), (alone, sums.tolist())
+    dist.barrier()
+    for r in range(world):
+        if r != rank:
+            ctx.shared_close(ptrs[r])
+    dist.barrier()
+    ctx.shared_free(mine)
+    ctx.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTIGPU_OK world=%d" % world)
+
+
+if __name__ == "__main__":
+    main()
