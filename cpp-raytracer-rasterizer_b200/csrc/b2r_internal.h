@@ -140,7 +140,7 @@ struct Ctx {
     // outputs kept on the device between draw and resolve / host copies
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
-    DevBuf rasTri, rasRows, rasKeys, rasScratch;
+    DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
     size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
     void* rasKeysCleanPtr = nullptr;
     // pinned staging for host-pointer entry points

@@ -20,21 +20,19 @@
 // depth test, so it is replayed step by step, never re-associated.
 //
 // Pipeline (v2):
-//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 16 rows
+//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 12 rows
 //                 (the 1M-triangle regime) are finished here: the three edge walks
-//                 (x and zinv chains only) update per-row left/right ends kept in
-//                 shared memory, then every on-screen fragment goes to the key
-//                 buffer with atomicMax -- no per-triangle, per-edge or per-row
-//                 intermediate ever reaches HBM.  Larger triangles are appended to
-//                 a compact list (setup record + row/edge-sample counts).
+//                 update per-row left/right ends kept in shared memory, then every
+//                 on-screen fragment goes to the key buffer with atomicMax.  The only
+//                 intermediate that reaches HBM is one 32-byte row record per polygon
+//                 row (fixed slot, no allocation pass).  Larger triangles are appended
+//                 to a compact list (setup record + row/edge-sample counts).
 //   big path      only for the listed large triangles: exclusive scan of the counts,
 //                 ras_edges (1 thread / triangle-edge, stores every edge sample),
 //                 ras_rows (1 lane / polygon row; short rows per lane, long rows
 //                 cooperatively across the warp).
-//   ras_shade     1 thread / pixel, streaming: key -> winner.  Small winners recompute
-//                 their row ends from the raw triangle (same 64-byte record that holds
-//                 the colour and normal the shader needs anyway); large winners read
-//                 their row record.  PixelShader in reference order, coalesced writes.
+//   ras_shade     1 thread / pixel, streaming: key -> winner -> its row record ->
+//                 PixelShader in reference order, coalesced writes; clears the key.
 #include <limits.h>
 
 #include "b2r_internal.h"
@@ -103,54 +101,76 @@ __device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, 
 
 // ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
 constexpr int kSmallRows = 16;      // triangles up to this many polygon rows never leave the SM
-constexpr int kSmallThreads = 128;
+constexpr int kSmallThreads = 64;
 
 struct RasCounters {
     unsigned nBig, bigRows, bigSamples, err;
     unsigned long long pad;
 };
 
-// Projected vertices of a small triangle (VertexShader output, :532-546), kept for the shade pass: 64 bytes.
-// pos3d.z is omitted: it is pos.z/pos.z == 1.0f exactly for every triangle that passes the coordinate
-// limits, and Interpolate's z step is then (1-1)/n == 0, so the chain stays 1.0f.
-struct VsRec {
-    int x[3], y[3];
-    float z[3], px[3], py[3];
-    int pad;
+// Row ends of one polygon row of a small triangle, written by ras_small for the shade pass: 32 bytes at the
+// fixed slot (triangle * kSmallRows + row), so no allocation pass is needed.  pos3d.z is omitted: it is
+// pos.z/pos.z == 1.0f exactly for every triangle that passes the coordinate limits, and Interpolate's z step is
+// then (1-1)/n == 0, so that chain stays 1.0f.
+struct SmallRow {
+    int lx, rx;
+    float lz, rz;
+    float lpx, lpy, rpx, rpy;
 };
 
-__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri) {
-    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(0xFFFFFFFFu - tri);
+// Depth key: larger zinv wins, then the lower triangle index (the reference's strict `>` in draw order, :606).
+// Bit 0 tells the shade pass which kind of row record the winner has; it cannot affect the order because it is
+// a function of the triangle index in the bits above it.  Triangle indices are below 2^31.
+__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri, unsigned big) {
+    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(((0x7FFFFFFFu - tri) << 1) | big);
+}
+__device__ __forceinline__ unsigned key_triangle(unsigned long long key) { return 0x7FFFFFFFu - ((unsigned)key >> 1); }
+// slot of polygon row y of small triangle tri: a small triangle spans at most kSmallRows consecutive rows,
+// so y modulo kSmallRows is unique within it
+__device__ __forceinline__ size_t small_row_slot(unsigned tri, int y) {
+    int m = y % kSmallRows;
+    if (m < 0) m += kSmallRows;
+    return (size_t)tri * kSmallRows + (size_t)m;
 }
 
-// One edge of Interpolate (:615-637) reduced to the two chains the depth test depends on.
+// One edge of Interpolate (:615-637): the x and zinv chains decide coverage and depth, the pos3d.xy chains
+// feed PixelShader (pos3d.z stays 1.0f, see SmallRow).
 struct EdgeStep {
     int n, sgn;
-    float cx, cz, sx, sz;
+    float cx, cz, cpx, cpy, sx, sz, spx, spy;
 };
-__device__ __forceinline__ EdgeStep edge_begin(int xa, int ya, float za, int xb, int yb, float zb) {
+__device__ __forceinline__ EdgeStep edge_begin(const RPixel& a, const RPixel& b) {
     EdgeStep e;
-    e.n = abs(ya - yb) + 1;                              // :712
-    e.sgn = (yb > ya) - (yb < ya);
+    e.n = abs(a.y - b.y) + 1;                            // :712
+    e.sgn = (b.y > a.y) - (b.y < a.y);
     const float div = (float)max(e.n - 1, 1);            // :622
-    e.sx = xdiv_step((float)(xb - xa), div);             // Pixel operator- / fPixel operator/
-    e.sz = xdiv_step(xsub(zb, za), div);
-    e.cx = (float)xa;                                    // fPixel(Pixel&)
-    e.cz = za;
+    e.sx = xdiv_step((float)(b.x - a.x), div);           // Pixel operator- / fPixel operator/
+    e.sz = xdiv_step(xsub(b.zinv, a.zinv), div);
+    e.spx = xdiv_step(xsub(b.p.x, a.p.x), div);
+    e.spy = xdiv_step(xsub(b.p.y, a.p.y), div);
+    e.cx = (float)a.x;                                   // fPixel(Pixel&)
+    e.cz = a.zinv;
+    e.cpx = a.p.x;
+    e.cpy = a.p.y;
     return e;
 }
 
 __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
                                                                    TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
-                                                                   int* __restrict__ bigSlot, VsRec* __restrict__ vsOut,
+                                                                   int2* __restrict__ triInfo, SmallRow* __restrict__ rowRec,
                                                                    RasCounters* __restrict__ ctr) {
     // per-thread row ends, [row][field][thread] so that a warp's accesses never conflict
     extern __shared__ int srow[];
     int* const mine = srow + threadIdx.x;
-    auto LX = [&](int r) -> int& { return mine[(4 * r + 0) * kSmallThreads]; };
-    auto RX = [&](int r) -> int& { return mine[(4 * r + 1) * kSmallThreads]; };
-    auto LZ = [&](int r) -> float& { return reinterpret_cast<float*>(mine)[(4 * r + 2) * kSmallThreads]; };
-    auto RZ = [&](int r) -> float& { return reinterpret_cast<float*>(mine)[(4 * r + 3) * kSmallThreads]; };
+    float* const minef = reinterpret_cast<float*>(mine);
+    auto LX = [&](int r) -> int& { return mine[(8 * r + 0) * kSmallThreads]; };
+    auto RX = [&](int r) -> int& { return mine[(8 * r + 1) * kSmallThreads]; };
+    auto LZ = [&](int r) -> float& { return minef[(8 * r + 2) * kSmallThreads]; };
+    auto RZ = [&](int r) -> float& { return minef[(8 * r + 3) * kSmallThreads]; };
+    auto LPX = [&](int r) -> float& { return minef[(8 * r + 4) * kSmallThreads]; };
+    auto LPY = [&](int r) -> float& { return minef[(8 * r + 5) * kSmallThreads]; };
+    auto RPX = [&](int r) -> float& { return minef[(8 * r + 6) * kSmallThreads]; };
+    auto RPY = [&](int r) -> float& { return minef[(8 * r + 7) * kSmallThreads]; };
 
     const int i = blockIdx.x * kSmallThreads + threadIdx.x;
     unsigned long long nTests = 0, nRows = 0, nDrawn = 0;
@@ -169,7 +189,6 @@ __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, u
         const int rows = maxY - minY + 1;  // :682
         if (bad || rows > kMaxRowsPerTriangle) {
             atomicExch(&ctr->err, 1u);  // the reference would try to allocate/walk an absurd row count
-            bigSlot[i] = -1;
         } else if (rows > kSmallRows) {
             const unsigned samples = (unsigned)(abs(v[0].y - v[1].y) + abs(v[1].y - v[2].y) + abs(v[2].y - v[0].y) + 3);
             const unsigned slot = atomicAdd(&ctr->nBig, 1u);
@@ -191,20 +210,13 @@ __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, u
             s.tri = i;
             bigTs[slot] = s;
             bigCounts[slot] = make_uint2((unsigned)rows, samples);
-            bigSlot[i] = (int)slot;
+            triInfo[i] = make_int2((int)slot, minY);
             nDrawn = 1;
             nRows = (unsigned long long)rows;
         } else {
-            bigSlot[i] = -1;
             nDrawn = 1;
             nRows = (unsigned long long)rows;
-            {
-                float4* o = reinterpret_cast<float4*>(vsOut + i);
-                o[0] = make_float4(__int_as_float(v[0].x), __int_as_float(v[1].x), __int_as_float(v[2].x), __int_as_float(v[0].y));
-                o[1] = make_float4(__int_as_float(v[1].y), __int_as_float(v[2].y), v[0].zinv, v[1].zinv);
-                o[2] = make_float4(v[2].zinv, v[0].p.x, v[1].p.x, v[2].p.x);
-                o[3] = make_float4(v[0].p.y, v[1].p.y, v[2].p.y, 0.f);
-            }
+            const int r0 = max(0, a.y0 - minY), r1 = min(rows, a.y1 - minY);  // rows of this band (DrawRows :743)
             for (int r = 0; r < rows; ++r) {  // :694-698
                 LX(r) = INT_MAX;
                 RX(r) = -INT_MAX;
@@ -214,41 +226,49 @@ __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, u
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
                 const int j = (e + 1) % 3;
-                EdgeStep st = edge_begin(v[e].x, v[e].y, v[e].zinv, v[j].x, v[j].y, v[j].zinv);
+                EdgeStep st = edge_begin(v[e], v[j]);
                 int r = v[e].y - minY;
                 for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
                     const int x = f2i_x86(st.cx);
                     if (x < LX(r)) {
                         LX(r) = x;
                         LZ(r) = st.cz;
+                        LPX(r) = st.cpx;
+                        LPY(r) = st.cpy;
                     }
                     if (x > RX(r)) {
                         RX(r) = x;
                         RZ(r) = st.cz;
+                        RPX(r) = st.cpx;
+                        RPY(r) = st.cpy;
                     }
                     st.cx = xadd(st.cx, st.sx);
                     st.cz = xadd(st.cz, st.sz);
+                    st.cpx = xadd(st.cpx, st.spx);
+                    st.cpy = xadd(st.cpy, st.spy);
                     r += st.sgn;
                 }
             }
             // DrawRows / DrawLineSDL / Bresenham with dy == 0 (:738-753, :592-612, :639-672)
-            const int r0 = max(0, a.y0 - minY), r1 = min(rows, a.y1 - minY);
             for (int r = r0; r < r1; ++r) {
-                const int lx = LX(r), pixels = RX(r) - lx;       // :598
-                const float lz = LZ(r);
-                const float zstep = xdiv(xsub(RZ(r), lz), (float)pixels);  // :648
+                const int lx = LX(r), rx = RX(r), pixels = rx - lx;  // :598
+                const float lz = LZ(r), rz = RZ(r);
+                {   // one full 32-byte sector per row, for the shade pass
+                    float4* rec = reinterpret_cast<float4*>(rowRec + small_row_slot((unsigned)i, minY + r));
+                    rec[0] = make_float4(__int_as_float(lx), __int_as_float(rx), lz, rz);
+                    rec[1] = make_float4(LPX(r), LPY(r), RPX(r), RPY(r));
+                }
+                const float zstep = xdiv(xsub(rz, lz), (float)pixels);  // :648
                 const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
                 unsigned long long* keyRow = keys + (size_t)(minY + r - a.y0) * (size_t)a.W;
                 for (int q = i0; q < i1; ++q) {
                     const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
                     if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
-                        atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i));
+                        atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i, 0u));
                 }
                 if (i1 > i0) nTests += (unsigned long long)(i1 - i0);
             }
         }
-    } else if (i < a.T) {
-        bigSlot[i] = -1;
     }
     if (a.stats) {
         for (int off = 16; off > 0; off >>= 1) {
@@ -404,7 +424,7 @@ __device__ __forceinline__ void raster_span(unsigned long long* __restrict__ key
     for (int i = i0; i < i1; i += istride) {
         const float zinv = xadd(lz, xmul(zstep, (float)i));  // :667
         if (zinv > 0.0f)                                     // :606 against a buffer cleared to 0 (:188)
-            atomicMax(keyRow + (lx + 1 + i), pack_key(zinv, tri));
+            atomicMax(keyRow + (lx + 1 + i), pack_key(zinv, tri, 1u));
     }
 }
 
@@ -464,121 +484,119 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
 }
 
 // ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------------------------
-// Row ends of row y of a small triangle from its projected vertices: each edge that spans the row is
-// walked (the x, zinv and pos3d.xy chains of Interpolate) to its sample on that row.
-__device__ __forceinline__ RowRec small_triangle_row(const VsRec* __restrict__ rec, int y) {
-    const float4* q = reinterpret_cast<const float4*>(rec);
-    const float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
-    const int vx[3] = {__float_as_int(q0.x), __float_as_int(q0.y), __float_as_int(q0.z)};
-    const int vy[3] = {__float_as_int(q0.w), __float_as_int(q1.x), __float_as_int(q1.y)};
-    const float vz[3] = {q1.z, q1.w, q2.x};
-    const float px[3] = {q2.y, q2.z, q2.w}, py[3] = {q3.x, q3.y, q3.z};
+// Loads of one pixel's winner: its row ends and the triangle's normal/colour.
+struct ShadeIn {
     RowRec r;
-    r.lx = INT_MAX;    // :696
-    r.rx = -INT_MAX;   // :697
-    r.lz = r.rz = 0.f;
-    r.lp[0] = r.lp[1] = r.rp[0] = r.rp[1] = 0.f;
-    r.lp[2] = r.rp[2] = 1.0f;
-    r.pad[0] = r.pad[1] = 0;
-#pragma unroll
-    for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
-        const int j = (e + 1) % 3;
-        const int ya = vy[e], yb = vy[j];
-        if (y < min(ya, yb) || y > max(ya, yb)) continue;
-        const int n = abs(ya - yb) + 1;            // :712
-        const float div = (float)max(n - 1, 1);    // :622
-        const float sx = xdiv_step((float)(vx[j] - vx[e]), div);
-        const float sz = xdiv_step(xsub(vz[j], vz[e]), div);
-        const float spx = xdiv_step(xsub(px[j], px[e]), div), spy = xdiv_step(xsub(py[j], py[e]), div);
-        float cx = (float)vx[e], cz = vz[e], cpx = px[e], cpy = py[e];
-        const int steps = abs(y - ya);
-        for (int k = 0; k < steps; ++k) {          // :632-635
-            cx = xadd(cx, sx);
-            cz = xadd(cz, sz);
-            cpx = xadd(cpx, spx);
-            cpy = xadd(cpy, spy);
-        }
-        const int x = f2i_x86(cx);
-        if (x < r.lx) {  // :718
-            r.lx = x;
-            r.lz = cz;
-            r.lp[0] = cpx; r.lp[1] = cpy;
-        }
-        if (x > r.rx) {  // :726
-            r.rx = x;
-            r.rz = cz;
-            r.rp[0] = cpx; r.rp[1] = cpy;
-        }
+    V3 normal, color;
+};
+__device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long long key, int y,
+                                               const TriSetup* __restrict__ bigTs, const int2* __restrict__ triInfo,
+                                               const SmallRow* __restrict__ rowRec, const RowRec* __restrict__ rows) {
+    ShadeIn in;
+    const unsigned tri = key_triangle(key);
+    const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
+    if (key & 1ull) {
+        const int2 info = triInfo[tri];  // (slot in the large-triangle list, minY)
+        in.r = rows[bigTs[info.x].rowBase + (unsigned)(y - info.y)];
+    } else {
+        const float4* q = reinterpret_cast<const float4*>(rowRec + small_row_slot(tri, y));
+        const float4 q0 = q[0], q1 = q[1];
+        in.r.lx = __float_as_int(q0.x);
+        in.r.rx = __float_as_int(q0.y);
+        in.r.lz = q0.z;
+        in.r.rz = q0.w;
+        in.r.lp[0] = q1.x; in.r.lp[1] = q1.y; in.r.lp[2] = 1.0f;
+        in.r.rp[0] = q1.z; in.r.rp[1] = q1.w; in.r.rp[2] = 1.0f;
+        in.r.pad[0] = in.r.pad[1] = 0;
     }
-    return r;
+    in.normal = mk3(t[9], t[10], t[11]);
+    in.color = mk3(t[12], t[13], t[14]);
+    return in;
 }
 
+// PixelShader (:549-589) for the fragment of pixel x on the winner's row.
+__device__ __forceinline__ void shade_pixel(const DevFrame* __restrict__ f, const ShadeIn& in, int x, float& depth,
+                                            float& focal, V3& colour) {
+    const RowRec& r = in.r;
+    const int pixels = r.rx - r.lx;
+    const float fi = (float)(x - r.lx - 1);
+    const float fdx = (float)pixels;
+    const float zinv = xadd(r.lz, xmul(xdiv(xsub(r.rz, r.lz), fdx), fi));                    // :648,667
+    const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
+    const V3 pos3d = xadd3(lp, xscale3(xdivs3(xsub3(rp, lp), fdx), fi));                     // :649,668
+    depth = zinv;  // == the key's high word
+    const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
+    V3 P = xdivs3(pos3d, zinv);        // :557
+    P = xvec_mat(P, f->Rinv);          // :559
+    P = xadd3(P, cam);                 // :560
+    const V3 dc = xsub3(cam, P);       // glm::distance(pPos3d, cameraPos) = length(cameraPos - pPos3d)
+    focal = xsub(xsqrt(xdot3(dc, dc)), f->dofFocal);  // :564-565
+    V3 result = mk3(0.f, 0.f, 0.f);
+    for (int k = 0; k < f->nLights; ++k) {  // :567-584
+        const V3 L = mk3(f->lightPos[k][0], f->lightPos[k][1], f->lightPos[k][2]);
+        const V3 dl = xsub3(L, P);
+        const float r2 = xdot3(dl, dl);
+        const float rr = xsqrt(r2);                        // :575
+        const float A = sphere_area(rr);                   // :576
+        const V3 lc = mk3(f->lightColor[k][0], f->lightColor[k][1], f->lightColor[k][2]);  // :577
+        const V3 rDir = xscale3(dl, xdiv(1.0f, rr));       // :578
+        const V3 B = xdivs3_shared(lc, A);                 // :580
+        const V3 D = xscale3(B, std_max(xdot3(rDir, in.normal), 0.0f));  // :582 (normal not re-normalised)
+        result = xadd3(result, D);
+    }
+    const V3 refl = mk3(f->reflectance[0], f->reflectance[1], f->reflectance[2]);
+    const V3 ind = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
+    colour = xmul3(xmul3(refl, xadd3(result, ind)), in.color);  // :587
+}
+
+// kShadePixels pixels per thread (256 apart in x, so every access stays coalesced): the key loads of all of them
+// are issued first, then all row-record / triangle loads, then the arithmetic -- the kernel is bound by the
+// latency of that dependent load chain, not by bandwidth.
+constexpr int kShadePixels = 2;
+
 __global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
-                                                        const int* __restrict__ bigSlot, const VsRec* __restrict__ vs,
+                                                        const int2* __restrict__ triInfo,
+                                                        const SmallRow* __restrict__ rowRec,
                                                         const RowRec* __restrict__ rows,
                                                         unsigned long long* __restrict__ keys) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = a.y0 + blockIdx.y;
-    if (x >= a.W || y >= a.y1) return;
-    const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
-    const size_t kidx = (size_t)(y - a.y0) * (size_t)a.W + (size_t)x;
-    const unsigned long long key = keys[kidx];
-    if (key != 0ull) keys[kidx] = 0ull;  // depthBuffer = 0 (:188) for the next frame, in the same pass
-    float depth = 0.f, focal = 0.f;
-    V3 colour = mk3(0.f, 0.f, 0.f);
-    int winner = -1;
-    if (key != 0ull) {
-        const DevFrame* __restrict__ f = a.frame;
-        const unsigned tri = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-        winner = (int)tri;
-        const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
-        const int slot = bigSlot[tri];
-        RowRec r;
-        if (slot >= 0) {
-            const TriSetup* s = bigTs + slot;
-            r = rows[s->rowBase + (unsigned)(y - s->minY)];
-        } else {
-            r = small_triangle_row(vs + tri, y);
-        }
-        const int pixels = r.rx - r.lx;
-        const float fi = (float)(x - r.lx - 1);
-        const float fdx = (float)pixels;
-        const float zinv = xadd(r.lz, xmul(xdiv(xsub(r.rz, r.lz), fdx), fi));                    // :648,667
-        const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
-        const V3 pos3d = xadd3(lp, xscale3(xdivs3(xsub3(rp, lp), fdx), fi));                     // :649,668
-        depth = zinv;  // == the key's high word
-        const V3 normal = mk3(t[9], t[10], t[11]), color = mk3(t[12], t[13], t[14]);
-        const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
-        V3 P = xdivs3(pos3d, zinv);        // :557
-        P = xvec_mat(P, f->Rinv);          // :559
-        P = xadd3(P, cam);                 // :560
-        const V3 dc = xsub3(cam, P);       // glm::distance(pPos3d, cameraPos) = length(cameraPos - pPos3d)
-        focal = xsub(xsqrt(xdot3(dc, dc)), f->dofFocal);  // :564-565
-        V3 result = mk3(0.f, 0.f, 0.f);
-        for (int k = 0; k < f->nLights; ++k) {  // :567-584
-            const V3 L = mk3(f->lightPos[k][0], f->lightPos[k][1], f->lightPos[k][2]);
-            const V3 dl = xsub3(L, P);
-            const float r2 = xdot3(dl, dl);
-            const float rr = xsqrt(r2);                        // :575
-            const float A = sphere_area(rr);                   // :576
-            const V3 lc = mk3(f->lightColor[k][0], f->lightColor[k][1], f->lightColor[k][2]);  // :577
-            const V3 rDir = xscale3(dl, xdiv(1.0f, rr));       // :578
-            const V3 B = xdivs3_shared(lc, A);                 // :580
-            const V3 D = xscale3(B, std_max(xdot3(rDir, normal), 0.0f));  // :582 (normal not re-normalised)
-            result = xadd3(result, D);
-        }
-        const V3 refl = mk3(f->reflectance[0], f->reflectance[1], f->reflectance[2]);
-        const V3 ind = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
-        colour = xmul3(xmul3(refl, xadd3(result, ind)), color);  // :587
+    const int xbase = blockIdx.x * (256 * kShadePixels) + threadIdx.x;
+    unsigned long long key[kShadePixels];
+#pragma unroll
+    for (int p = 0; p < kShadePixels; ++p) {
+        const int x = xbase + 256 * p;
+        key[p] = (x < a.W) ? keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x] : 0ull;
     }
-    if (a.depth) a.depth[idx] = depth;
-    if (a.colours) {
-        a.colours[3 * idx] = colour.x;
-        a.colours[3 * idx + 1] = colour.y;
-        a.colours[3 * idx + 2] = colour.z;
+    ShadeIn in[kShadePixels];
+#pragma unroll
+    for (int p = 0; p < kShadePixels; ++p) {
+        const int x = xbase + 256 * p;
+        if (key[p] != 0ull) {
+            keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x] = 0ull;  // depthBuffer = 0 (:188) for the next frame
+            in[p] = shade_fetch(a, key[p], y, bigTs, triInfo, rowRec, rows);
+        }
     }
-    if (a.focal) a.focal[idx] = focal;
-    if (a.winner) a.winner[idx] = winner;
+#pragma unroll
+    for (int p = 0; p < kShadePixels; ++p) {
+        const int x = xbase + 256 * p;
+        if (x >= a.W) continue;
+        float depth = 0.f, focal = 0.f;
+        V3 colour = mk3(0.f, 0.f, 0.f);
+        int winner = -1;
+        if (key[p] != 0ull) {
+            winner = (int)key_triangle(key[p]);
+            shade_pixel(a.frame, in[p], x, depth, focal, colour);
+        }
+        const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
+        if (a.depth) a.depth[idx] = depth;
+        if (a.colours) {
+            a.colours[3 * idx] = colour.x;
+            a.colours[3 * idx + 1] = colour.y;
+            a.colours[3 * idx + 2] = colour.z;
+        }
+        if (a.focal) a.focal[idx] = focal;
+        if (a.winner) a.winner[idx] = winner;
+    }
 }
 
 // ---- culling block of Update() (:385-447) ------------------------------------
@@ -650,13 +668,14 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     const int T = a.T;
     const int bandH = a.y1 - a.y0;
     cudaError_t e;
-    // scratch: [counters 64 B][bigCounts uint2 x T][excl uint2 x T][blockSums][totals]; bigSlot int x T separately
+    // scratch: [counters 64 B][bigCounts uint2 x T][excl uint2 x T][blockSums][totals]; triInfo int2 x T separately
     const int nbMax = (T + kScanBlock - 1) / kScanBlock + 1;
     const size_t offCtr = 0, offCounts = 256, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
                  offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
                  offTotals = align_up(offSums + sizeof(uint2) * (size_t)nbMax, 256), scratchBytes = offTotals + 256;
     if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
-    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int) * (size_t)(T + 1) + sizeof(VsRec) * (size_t)(T + 1) + 1024)) != cudaSuccess) return e;
+    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int2) * (size_t)(T + 1) + 1024)) != cudaSuccess) return e;
+    if ((e = c->rasSmall.reserve(sizeof(SmallRow) * (size_t)kSmallRows * (size_t)(T + 1))) != cudaSuccess) return e;
     if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
     unsigned char* sc = c->rasScratch.as<unsigned char>();
     RasCounters* ctr = reinterpret_cast<RasCounters*>(sc + offCtr);
@@ -664,9 +683,9 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     uint2* excl = reinterpret_cast<uint2*>(sc + offExcl);
     uint2* sums = reinterpret_cast<uint2*>(sc + offSums);
     uint2* totals = reinterpret_cast<uint2*>(sc + offTotals);
-    int* bigSlot = c->rasTri.as<int>();
-    VsRec* vs = reinterpret_cast<VsRec*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int) * (size_t)(T + 1), 256));
-    TriSetup* ts = reinterpret_cast<TriSetup*>(reinterpret_cast<unsigned char*>(vs) + align_up(sizeof(VsRec) * (size_t)(T + 1), 256));
+    int2* triInfo = c->rasTri.as<int2>();
+    SmallRow* rowRec = c->rasSmall.as<SmallRow>();
+    TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int2) * (size_t)(T + 1), 256));
     unsigned long long* keys = c->rasKeys.as<unsigned long long>();
 
     if ((e = cudaMemsetAsync(ctr, 0, sizeof(RasCounters), s)) != cudaSuccess) return e;
@@ -680,13 +699,13 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     RasCounters host{};
     const RowRec* rowsPtr = nullptr;
     if (T > 0) {
-        const size_t smem = sizeof(int) * 4 * kSmallRows * kSmallThreads;
+        const size_t smem = sizeof(int) * 8 * kSmallRows * kSmallThreads;
         static bool attrSet = false;
         if (!attrSet) {
             if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
             attrSet = true;
         }
-        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, bigSlot, vs, ctr);
+        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, triInfo, rowRec, ctr);
         c->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         // how many large triangles / rows / edge samples: 16 bytes back to size the big path
@@ -717,8 +736,8 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     {
-        dim3 grid((a.W + 255) / 256, bandH);
-        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, bigSlot, vs, rowsPtr, keys);
+        dim3 grid((a.W + 256 * kShadePixels - 1) / (256 * kShadePixels), bandH);
+        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, triInfo, rowRec, rowsPtr, keys);
         c->launches++;
     }
     e = cudaGetLastError();
