@@ -155,7 +155,7 @@ int b2r_destroy(b2r_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
-                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->stats};
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->stats};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
@@ -345,6 +345,7 @@ int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_int
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
     a.geom = c->geom.as<float4>();
+    a.xconst = a.fconst = nullptr;
     a.frame = c->frame.as<DevFrame>();
     a.T = c->T;
     a.W = c->W;
@@ -360,7 +361,7 @@ int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_int
     a.useFilter = c->optRtFilter;
     cudaError_t e = launch_rt_trace_shade(c, a, c->stream);
     if (e == cudaErrorInvalidConfiguration)
-        return fail(c, B2R_E_UNSUPPORTED, "raytracer: triangles x ray origins exceed the shared-memory resident limit of this build");
+        return fail(c, B2R_E_UNSUPPORTED, "raytracer: more than ~100,000 triangles per scene are not supported by the brute-force tracer");
     if (e != cudaSuccess) return cuda_fail(c, e, "rt_trace_shade_kernel");
     return B2R_OK;
 }

@@ -52,6 +52,8 @@ constexpr int kOriginQuads = 5;
 
 struct RtLaunch {
     const float4* geom;      // T * kGeomQuads
+    const float4* xconst;    // large scenes only: nO * T * 2 exact (origin,triangle) constants in HBM
+    const float4* fconst;    // large scenes only: nO * T * 3 filter forms in HBM
     const DevFrame* frame;
     int T;
     int W, H, y0, y1;
@@ -141,6 +143,7 @@ struct Ctx {
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
+    DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
     size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
     void* rasKeysCleanPtr = nullptr;
     // pinned staging for host-pointer entry points

@@ -334,9 +334,39 @@ __device__ __forceinline__ float warp_min(float v) { return ord2f(__reduce_min_s
 __device__ __forceinline__ float warp_max(float v) { return ord2f(__reduce_max_sync(kFull, f2ord(v))); }
 
 // ---------------------------------------------------------------------------
-// The kernel.  TILECULL = false keeps only the per-ray filter (every ray looks at every triangle).
+// Per (origin, triangle) constants for one pair: exact part (2 quads) and filter forms (3 quads).
+__device__ __forceinline__ void write_pair_constants(const float4* __restrict__ g, float4 og, bool primary,
+                                                     const DevFrame* __restrict__ f, bool withForms,
+                                                     float4* __restrict__ X, float4* __restrict__ F) {
+    const TriG t = load_geom(g);
+    const OriginTri c = origin_constants(t.v0, t.e1, t.e2, t.n, mk3(og.x, og.y, og.z));
+    X[0] = make_float4(c.be2.x, c.be2.y, c.be2.z, c.nb);
+    X[1] = make_float4(c.e1b.x, c.e1b.y, c.e1b.z, 0.f);
+    if (withForms) {
+        float q[9];
+        filter_forms(t.n, c.be2, c.e1b, c.nb, primary, f->R, f->focal, f->primaryDmax, q);
+        F[0] = make_float4(q[0], q[1], q[2], 0.f);
+        F[1] = make_float4(q[3], q[4], q[5], 0.f);
+        F[2] = make_float4(q[6], q[7], q[8], 0.f);
+    }
+}
+
+// Scenes too large for shared memory: the same constants, once per frame, into HBM (read back through L1/L2).
+__global__ void __launch_bounds__(256) rt_origin_setup_kernel(const float4* __restrict__ geom, const DevFrame* __restrict__ f,
+                                                              int T, int withForms, float4* __restrict__ X,
+                                                              float4* __restrict__ F) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= f->nOrigins * T) return;
+    const int o = it / T, i = it - o * T;
+    const float4 og = make_float4(f->origin[o][0], f->origin[o][1], f->origin[o][2], 0.f);
+    write_pair_constants(geom + (size_t)i * kGeomQuads, og, o == 0, f, withForms != 0, X + 2 * (size_t)it, F + 3 * (size_t)it);
+}
+
 // ---------------------------------------------------------------------------
-template <bool TILECULL, bool FILTER, bool STATS>
+// The kernel.  RESIDENT: triangles and constants live in shared memory (staged/computed per CTA); otherwise they
+// are read from HBM.  TILECULL = false keeps only the per-ray filter (every ray looks at every triangle).
+// ---------------------------------------------------------------------------
+template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS>
 __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -344,47 +374,48 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     const DevFrame* __restrict__ f = a.frame;
     const int nO = f->nOrigins;
     const int nChunks = (T + 31) >> 5;
-    float4* sG = reinterpret_cast<float4*>(smem_raw);        // T * kGeomQuads   scene-static triangle records
-    float4* sX = sG + (size_t)T * kGeomQuads;                // nO * T * 2       exact (origin,triangle) constants
-    float4* sF = sX + (size_t)nO * T * 2;                    // nO * T * 3       filter forms
-    float4* sOrg = sF + (size_t)nO * T * 3;                  // nO               ray origins
-    float4* sPow = sOrg + nO;                                // nLights          light powers
-    unsigned* sTileMask = reinterpret_cast<unsigned*>(sPow + f->nLights);  // 8 warps * nChunks
-
-    // 1. triangles: HBM -> shared memory by one bulk async copy (TMA), completion on an mbarrier
-    const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
+    const float4 *sG, *sX, *sF;  // triangle records, exact (origin,triangle) constants, filter forms
+    float4* sOrg;                // nO ray origins, then nLights light powers, then the per-warp tile lists
+    if constexpr (RESIDENT) {
+        float4* g = reinterpret_cast<float4*>(smem_raw);   // T * kGeomQuads
+        float4* x = g + (size_t)T * kGeomQuads;            // nO * T * 2
+        float4* ff = x + (size_t)nO * T * 2;               // nO * T * 3
+        sOrg = ff + (size_t)nO * T * 3;
+        // 1. triangles: HBM -> shared memory by one bulk async copy (TMA), completion on an mbarrier
+        const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && geomBytes) {
+            mbar_expect_tx(&bar, geomBytes);
+            bulk_g2s(g, a.geom, geomBytes, &bar);
+        }
+        for (int i = threadIdx.x; i < nO; i += kThreads)
+            sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
+        if (geomBytes) mbar_wait(&bar, 0);
+        __syncthreads();
+        // 2. per (origin, triangle) constants, once per CTA
+        for (int it = threadIdx.x; it < nO * T; it += kThreads) {
+            const int o = it / T, i = it - o * T;
+            write_pair_constants(g + (size_t)i * kGeomQuads, sOrg[o], o == 0, f, FILTER, x + 2 * it, ff + 3 * it);
+        }
+        sG = g;
+        sX = x;
+        sF = ff;
+    } else {
+        sG = a.geom;
+        sX = a.xconst;
+        sF = a.fconst;
+        sOrg = reinterpret_cast<float4*>(smem_raw);
+        for (int i = threadIdx.x; i < nO; i += kThreads)
+            sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && geomBytes) {
-        mbar_expect_tx(&bar, geomBytes);
-        bulk_g2s(sG, a.geom, geomBytes, &bar);
-    }
-    for (int i = threadIdx.x; i < nO; i += kThreads)
-        sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
+    float4* sPow = sOrg + nO;
     for (int i = threadIdx.x; i < f->nLights; i += kThreads)
         sPow[i] = make_float4(f->lightPower[i][0], f->lightPower[i][1], f->lightPower[i][2], 0.f);
-    if (geomBytes) mbar_wait(&bar, 0);
-    __syncthreads();
-
-    // 2. per (origin, triangle) constants, once per CTA
-    for (int it = threadIdx.x; it < nO * T; it += kThreads) {
-        const int o = it / T, i = it - o * T;
-        const TriG t = load_geom(sG + (size_t)i * kGeomQuads);
-        const float4 og = sOrg[o];
-        const OriginTri c = origin_constants(t.v0, t.e1, t.e2, t.n, mk3(og.x, og.y, og.z));
-        sX[2 * it] = make_float4(c.be2.x, c.be2.y, c.be2.z, c.nb);
-        sX[2 * it + 1] = make_float4(c.e1b.x, c.e1b.y, c.e1b.z, 0.f);
-        if (FILTER) {
-            float q[9];
-            filter_forms(t.n, c.be2, c.e1b, c.nb, o == 0, f->R, f->focal, f->primaryDmax, q);
-            sF[3 * it] = make_float4(q[0], q[1], q[2], 0.f);
-            sF[3 * it + 1] = make_float4(q[3], q[4], q[5], 0.f);
-            sF[3 * it + 2] = make_float4(q[6], q[7], q[8], 0.f);
-        }
-    }
+    uint2* sTileList = reinterpret_cast<uint2*>(sPow + f->nLights);  // 8 warps * nChunks entries (chunk, mask)
     __syncthreads();
 
     const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
@@ -399,7 +430,8 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     const float invNN = (float)(N * N);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned* myTileMask = sTileMask + warp * nChunks;
+    uint2* myTileList = sTileList + warp * nChunks;  // non-empty chunks of this warp's tile
+    int nList = 0;
     Counters cnt;
     unsigned tile0 = 0u;  // tile mask of the only chunk when T <= 32
 
@@ -416,12 +448,18 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
             const float pad = (N > 1) ? 0.5f + 0.01f : 0.01f;
             const float cx = ((float)wx0 + 3.5f) - halfW, cy = ((float)wy0 + 1.5f) - halfH;
             const float hx = 3.5f + pad, hy = 1.5f + pad;
+            nList = 0;
             for (int c = 0; c < nChunks; ++c) {
                 unsigned m;
                 if (TILECULL) m = primary_tile_mask<FILTER>(sF, c * 32, T, lane, cx, cy, hx, hy);
                 else m = (T - c * 32 >= 32) ? kFull : ((1u << (T - c * 32)) - 1u);
-                if (nChunks > 1 && lane == 0) myTileMask[c] = m;
-                if (nChunks == 1) tile0 = m;
+                if (nChunks == 1) {
+                    tile0 = m;
+                    nList = 1;
+                } else if (m) {  // m is warp-uniform (a ballot)
+                    if (lane == 0) myTileList[nList] = make_uint2((unsigned)c, m);
+                    ++nList;
+                }
             }
             if (nChunks > 1) __syncwarp();
         }
@@ -443,10 +481,10 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                 bool any = false;
                 if (inside) {
                     if constexpr (STATS) cnt.primary++;
-                    for (int c = 0; c < nChunks; ++c) {
-                        const int base = c * 32;
-                        const unsigned tm = (nChunks > 1) ? myTileMask[c] : tile0;
-                        unsigned m = primary_ray_mask<FILTER>(sF, base, tm, dx, dy);
+                    for (int e = 0; e < nList; ++e) {
+                        const uint2 cm = (nChunks > 1) ? myTileList[e] : make_uint2(0u, tile0);
+                        const int base = (int)cm.x * 32;
+                        unsigned m = primary_ray_mask<FILTER>(sF, base, cm.y, dx, dy);
                         for (; m; m &= m - 1) {  // ascending triangle index
                             const int i = base + __ffs(m) - 1;
                             if constexpr (STATS) cnt.exact++;
@@ -574,15 +612,15 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     }
 }
 
-static size_t rt_smem_bytes(int T, int nO, int nLights) {
-    const size_t quads = (size_t)T * kGeomQuads + (size_t)nO * T * 5 + nO + nLights;
-    return quads * 16 + (size_t)(kThreads / 32) * ((T + 31) / 32) * 4 + 16;
+static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident) {
+    const size_t quads = (resident ? (size_t)T * kGeomQuads + (size_t)nO * T * 5 : 0) + nO + nLights;
+    return quads * 16 + (size_t)(kThreads / 32) * ((T + 31) / 32) * 8 + 16;
 }
 
-template <bool TILECULL>
+template <bool RESIDENT, bool TILECULL>
 static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
-    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<TILECULL, true, true> : rt_trace_shade_kernel<TILECULL, true, false>)
-                            : (a.stats ? rt_trace_shade_kernel<TILECULL, false, true> : rt_trace_shade_kernel<TILECULL, false, false>);
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true> : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false>)
+                            : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true> : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSM = 1;
@@ -597,12 +635,30 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
     return cudaGetLastError();
 }
 
-// B2R_OPT_RT_VARIANT: 0 = tile/warp culling + per-ray filter (default); 1 = per-ray filter only.
-cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s) {
+// B2R_OPT_RT_VARIANT: 0 = tile/warp culling + per-ray filter (default); 1 = per-ray filter only;
+// 2 = like 0 but constants read from HBM even when they would fit in shared memory (tests the large-scene path).
+cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const DevFrame& f = c->hostFrame;
-    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights);
-    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;  // reported as B2R_E_UNSUPPORTED by the caller
-    return c->optRtVariant == 1 ? launch_variant<false>(c, a, smem, s) : launch_variant<true>(c, a, smem, s);
+    RtLaunch a = a0;
+    const size_t smemRes = rt_smem_bytes(a.T, f.nOrigins, f.nLights, true);
+    const bool resident = smemRes <= 96 * 1024 && c->optRtVariant != 2;
+    if (resident) {
+        a.xconst = a.fconst = nullptr;
+        return c->optRtVariant == 1 ? launch_variant<true, false>(c, a, smemRes, s) : launch_variant<true, true>(c, a, smemRes, s);
+    }
+    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > ~100k triangles: reported as B2R_E_UNSUPPORTED
+    const size_t pairs = (size_t)f.nOrigins * (size_t)a.T;
+    cudaError_t e;
+    if ((e = c->rtX.reserve(pairs * 32 + 64)) != cudaSuccess) return e;
+    if ((e = c->rtF.reserve(pairs * 48 + 64)) != cudaSuccess) return e;
+    a.xconst = c->rtX.as<float4>();
+    a.fconst = c->rtF.as<float4>();
+    rt_origin_setup_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, s>>>(a.geom, a.frame, a.T, a.useFilter, c->rtX.as<float4>(),
+                                                                          c->rtF.as<float4>());
+    c->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return launch_variant<false, true>(c, a, smem, s);
 }
 
 }  // namespace b2r

@@ -198,3 +198,35 @@ def test_errors(pkg):
     with pytest.raises(pkg.B2RError):
         ctx.rt_draw(5, 40)  # band outside the screen
     ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_large_scene_path(pkg, oracle, variant):
+    """Scenes that do not fit in shared memory keep their per-frame constants in HBM (variant 2 forces that path
+    for a small scene too); 2,430 tessellated Cornell triangles with AA and two lights."""
+    w, h = 96, 64
+    tris = pkg.tessellate(pkg.cornell_box(), 9 if variant == 0 else 2)
+    fp = pkg.default_frame_params(0, w, h)
+    fp.aaEnabled, fp.aaSamples = 1, 2
+    fp.set_lights([[0, -0.5, -0.7, 1, 1, 1, 14], [0.4, -0.2, -0.9, 0.3, 0.6, 0.9, 6]])
+    ctx = pkg.Context(w, h)
+    ctx.set_option(pkg.capi.OPT_RT_VARIANT, variant)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    want = oracle.rt_draw(tris, fp, w, h)
+    for filt in (1, 0):
+        ctx.set_option(pkg.capi.OPT_RT_FILTER, filt)
+        check(ctx.rt_draw(), want)
+    ctx.close()
+
+
+def test_stl_sized_scene(pkg, oracle):
+    """~9k triangles (the size of the reference's enemy1.stl): the brute-force semantics still hold."""
+    w, h = 64, 40
+    tris = pkg.tessellate(pkg.cornell_box(), 17)  # 8,670 triangles
+    fp = pkg.default_frame_params(0, w, h)
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    check(ctx.rt_draw(), oracle.rt_draw(tris, fp, w, h))
+    ctx.close()
