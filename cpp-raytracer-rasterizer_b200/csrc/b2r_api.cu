@@ -159,6 +159,10 @@ int b2r_destroy(b2r_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
+    if (c->copyStream) {
+        cudaStreamDestroy(c->copyStream);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(c->partDone[i]);
+    }
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
     delete c;
     return B2R_OK;
@@ -336,11 +340,7 @@ int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds) {
 }
 
 // ---- raytracer ------------------------------------------------------------------
-int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc) {
-    Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (int rc = bind(c)) return rc;
-    if (int rc = check_band(c, y0, y1)) return rc;
-    if (int rc = reset_stats(c)) return rc;
+static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc) {
     c->lastDraw = 0;
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
@@ -366,26 +366,55 @@ int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_int
     return B2R_OK;
 }
 
+int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    return rt_launch_band(c, y0, y1, d_col, d_clo, d_foc);
+}
+
+// Host-buffer draw.  Large frames are cut into a few sub-bands so that the device-to-host copy of one
+// sub-band overlaps the tracing of the next (second stream + events); the arithmetic per pixel is unchanged.
 static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* clo, float* foc, uint32_t* surface) {
     if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
     const size_t n = (size_t)c->W * c->H;
     CU(c->colours.reserve(n * 12), "alloc pixelColours");
     if (clo) CU(c->closest.reserve(n * 20), "alloc closestIntersections");
     const bool needFocal = foc || (surface && c->params.dofEnabled);
     if (needFocal) CU(c->focal.reserve(n * 4), "alloc focalDistances");
-    if (int rc = b2r_rt_draw_device_async(reinterpret_cast<b2r_ctx*>(c), y0, y1, c->colours.as<float>(),
-                                          clo ? c->closest.as<b2r_intersection>() : nullptr,
-                                          needFocal ? c->focal.as<float>() : nullptr))
-        return rc;
-    if (surface) {
-        CU(c->surface.reserve(n * 4), "alloc surface");
-        CU(launch_resolve_surface(c, y0, y1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
-           "resolve_surface_kernel");
-        if (int rc = copy_rows_out(c, surface, c->surface.p, y0, y1, 4)) return rc;
+    if (surface) CU(c->surface.reserve(n * 4), "alloc surface");
+    const int rows = y1 - y0;
+    const bool anyOut = surface || col || clo || foc;
+    // the depth-of-field window reads rows of neighbouring sub-bands, so it resolves only after the whole draw
+    int parts = (!anyOut || (surface && c->params.dofEnabled)) ? 1 : (rows >= 1024 ? 4 : (rows >= 256 ? 2 : 1));
+    if (parts > 1 && !c->copyStream) {
+        CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking), "cudaStreamCreate (copy)");
+        for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->partDone[i], cudaEventDisableTiming), "cudaEventCreate");
     }
-    if (int rc = copy_rows_out(c, col, c->colours.p, y0, y1, 12)) return rc;
-    if (int rc = copy_rows_out(c, clo, c->closest.p, y0, y1, 20)) return rc;
-    if (int rc = copy_rows_out(c, foc, c->focal.p, y0, y1, 4)) return rc;
+    cudaStream_t drawStream = c->stream;
+    for (int p = 0; p < parts; ++p) {
+        const int a0 = y0 + (int)((long long)rows * p / parts), a1 = y0 + (int)((long long)rows * (p + 1) / parts);
+        if (int rc = rt_launch_band(c, a0, a1, c->colours.as<float>(), clo ? c->closest.as<b2r_intersection>() : nullptr,
+                                    needFocal ? c->focal.as<float>() : nullptr))
+            return rc;
+        if (surface)
+            CU(launch_resolve_surface(c, a0, a1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), drawStream),
+               "resolve_surface_kernel");
+        if (parts > 1) {
+            CU(cudaEventRecord(c->partDone[p], drawStream), "cudaEventRecord");
+            CU(cudaStreamWaitEvent(c->copyStream, c->partDone[p], 0), "cudaStreamWaitEvent");
+            c->stream = c->copyStream;  // copy_rows_out issues on c->stream
+        }
+        int rc = copy_rows_out(c, surface, c->surface.p, a0, a1, 4);
+        if (!rc) rc = copy_rows_out(c, col, c->colours.p, a0, a1, 12);
+        if (!rc) rc = copy_rows_out(c, clo, c->closest.p, a0, a1, 20);
+        if (!rc) rc = copy_rows_out(c, foc, c->focal.p, a0, a1, 4);
+        c->stream = drawStream;
+        if (rc) return rc;
+    }
+    if (parts > 1) CU(cudaStreamSynchronize(c->copyStream), "raytracer draw (copies)");
     CU(cudaStreamSynchronize(c->stream), "raytracer draw");
     return B2R_OK;
 }

@@ -122,6 +122,8 @@ struct Ctx {
     int smCount = 148;
     cudaStream_t ownStream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;   // host-buffer draws: D2H of one sub-band overlaps the next sub-band's kernels
+    cudaEvent_t partDone[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
     // scene
