@@ -137,5 +137,38 @@ def build(sizes=SIZES, verbose=True):
             raise SystemExit(1)
 
 
+def build_integration(sizes=((500, 500), (160, 120)), verbose=True):
+    """The reference programs THEMSELVES -- main(), Update(), LoadTestModel, SDLauxiliary.h -- with only the body of
+    Draw() replaced by the calls INTEGRATION.md gives (patch P8: the reference definition is renamed
+    Draw_reference and oracle/integration_draw_{rt,ras}.inc is appended).  Executables in oracle/_ref/, linked against
+    libb2r.so; tests/test_integration.py runs them on the GPU box with B2R_STUB_FRAMES=1 and compares the
+    screenshot.bmp their own main() writes with the oracle's frame."""
+    if not os.path.isdir(REF):
+        raise SystemExit(f"{REF} not present")
+    os.makedirs(OUT, exist_ok=True)
+    root = os.path.dirname(HERE)
+    libdir = os.path.join(root, "cpp-raytracer-rasterizer_b200", "lib")
+    glm = os.path.join(REF, "raytracer")
+    with tempfile.TemporaryDirectory(prefix="b2r_int_") as tmp:
+        for prog, srcdir, patch in (("raytracer", "raytracer/Source", patch_common), ("rasteriser", "rasteriser/Source", patch_common)):
+            src = open(os.path.join(REF, srcdir, prog + ".cpp")).read()
+            src = patch_common(src, 9 if prog == "raytracer" else 7)  # P1, P2 only: no oracle instrumentation here
+            src = _sub(src, r"\nvoid Draw\(\)\n\{", "\nvoid Draw_reference()\n{", 1, "P8")
+            inc = open(os.path.join(HERE, "integration_draw_rt.inc" if prog == "raytracer" else "integration_draw_ras.inc")).read()
+            patched = os.path.join(tmp, prog + "_b2r.cpp")
+            open(patched, "w").write("#include <cstring>\n#include <cstdint>\n" + src + "\n" + inc)
+            for (w, h) in sizes:
+                out = os.path.join(OUT, f"{prog}_b2r_{w}x{h}")
+                cmd = ["g++", "-fopenmp", "-O3", "-ffp-contract=off", "-w", "-std=gnu++14", f"-DREF_W={w}", f"-DREF_H={h}",
+                       "-I" + os.path.join(HERE, "sdl_stub"), "-I" + glm, "-I" + os.path.join(REF, srcdir),
+                       "-I" + os.path.join(root, "include"), patched, "-o", out, "-L" + libdir, "-lb2r",
+                       "-Wl,-rpath,$ORIGIN/../../cpp-raytracer-rasterizer_b200/lib"]
+                subprocess.check_call(cmd)
+                if verbose:
+                    print("built", os.path.relpath(out, HERE))
+
+
 if __name__ == "__main__":
     build()
+    if "--integration" in sys.argv:
+        build_integration()

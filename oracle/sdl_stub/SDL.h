@@ -13,6 +13,7 @@
 #define B2R_ORACLE_SDL_STUB_H
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -72,7 +73,22 @@ static inline SDL_Surface* SDL_SetVideoMode(int w, int h, int bpp, Uint32 flags)
     return s;
 }
 
-static inline int SDL_PollEvent(SDL_Event*) { return 0; }
+/* No events, except that with B2R_STUB_FRAMES=n in the environment the n-th event-pump round reports
+ * SDL_QUIT, so the reference's own `while( NoQuitMessageSDL() )` main loop ends after n iterations
+ * (used by the integration binaries, oracle/build_ref.py --integration). */
+static inline int SDL_PollEvent(SDL_Event* e) {
+    static long rounds = 0;
+    static long limit = -2;
+    if (limit == -2) {
+        const char* v = std::getenv("B2R_STUB_FRAMES");
+        limit = v ? std::atol(v) : -1;
+    }
+    if (limit >= 0 && ++rounds > limit) {
+        e->type = SDL_QUIT;
+        return 1;
+    }
+    return 0;
+}
 static inline Uint32 SDL_MapRGB(const SDL_PixelFormat*, Uint8 r, Uint8 g, Uint8 b) {
     return ((Uint32)r << 16) | ((Uint32)g << 8) | (Uint32)b;
 }
@@ -88,7 +104,32 @@ static inline Uint8* SDL_GetKeyState(int*) {
 static inline int SDL_LockSurface(SDL_Surface*) { return 0; }
 static inline void SDL_UnlockSurface(SDL_Surface*) {}
 static inline void SDL_UpdateRect(SDL_Surface*, int, int, Uint32, Uint32) {}
-static inline int SDL_SaveBMP(SDL_Surface*, const char*) { return 0; }
+/* 24-bit bottom-up BMP of the XRGB surface, rows padded to 4 bytes, 54-byte header: what SDL 1.2 writes. */
+static inline int SDL_SaveBMP(SDL_Surface* s, const char* path) {
+    std::FILE* f = std::fopen(path, "wb");
+    if (!f) return -1;
+    const Uint32 pitch = (Uint32)((s->w * 3 + 3) & ~3), size = pitch * (Uint32)s->h;
+    unsigned char h[54];
+    std::memset(h, 0, sizeof h);
+    h[0] = 'B'; h[1] = 'M';
+    const Uint32 fields[][2] = {{2, 54u + size}, {10, 54u}, {14, 40u}, {18, (Uint32)s->w}, {22, (Uint32)s->h}, {34, size}};
+    for (const auto& fd : fields)
+        for (int b = 0; b < 4; ++b) h[fd[0] + b] = (unsigned char)(fd[1] >> (8 * b));
+    h[26] = 1; h[28] = 24;
+    std::fwrite(h, 1, 54, f);
+    unsigned char* row = (unsigned char*)std::calloc(pitch, 1);
+    for (int y = s->h - 1; y >= 0; --y) {
+        const Uint32* px = (const Uint32*)s->pixels + (size_t)y * (s->pitch / 4);
+        for (int x = 0; x < s->w; ++x) {
+            row[3 * x] = (unsigned char)(px[x] & 0xFF);
+            row[3 * x + 1] = (unsigned char)((px[x] >> 8) & 0xFF);
+            row[3 * x + 2] = (unsigned char)((px[x] >> 16) & 0xFF);
+        }
+        std::fwrite(row, 1, pitch, f);
+    }
+    std::free(row);
+    return std::fclose(f);
+}
 static inline int SDL_FillRect(SDL_Surface* s, void*, Uint32 c) {
     Uint32* p = (Uint32*)s->pixels;
     for (size_t i = 0, n = (size_t)s->w * (size_t)s->h; i < n; ++i) p[i] = c;
