@@ -146,7 +146,8 @@ __device__ __forceinline__ TriG load_geom(const float4* g) {
 constexpr float kShadowMargin = 1.0001f;
 
 __host__ __device__ inline void filter_forms(V3 n, V3 be2, V3 e1b, float nb, bool primary, const float* R,
-                                             float focal, float primaryDmax, float* out) {
+                                             float focal, float primaryDmax, float* out, double* invMout = nullptr) {
+    if (invMout) *invMout = 0.0;
     double s = (nb > 0.f) ? 1.0 : ((nb < 0.f) ? -1.0 : 0.0);
     if (fabsf(nb) < 7.9e-31f) s = 0.0;  // 2^-100: t = nb/d0 could flush to +-0, which `t >= 0` accepts
     const double L1 = fabs((double)n.x) + fabs((double)n.y) + fabs((double)n.z) + fabs((double)be2.x) +
@@ -155,6 +156,7 @@ __host__ __device__ inline void filter_forms(V3 n, V3 be2, V3 e1b, float nb, boo
     bool ok = (s != 0.0) && (L1 > 8.7e-19) && (L1 < 1.1e18);  // 2^-60 .. 2^60; false for NaN/inf
     if (ok) {
         const double invM = 262144.0 / L1;  // 1/M
+        if (invMout) *invMout = invM;
         // forms in terms of dir:  c_k . dir  with c_k = -s * vec_k / M  (d_k = vec_k . (-dir), raytracer.cpp:232-234)
         const double c[3][3] = {
             {-s * be2.x * invM, -s * be2.y * invM, -s * be2.z * invM},
@@ -177,6 +179,7 @@ __host__ __device__ inline void filter_forms(V3 n, V3 be2, V3 e1b, float nb, boo
             ok = ok && isfinite(out[3 * k]) && isfinite(out[3 * k + 1]) && isfinite(out[3 * k + 2]);
         }
     }
+    if (!ok && invMout) *invMout = 0.0;
     if (!ok)  // always a candidate: the exact path decides
         for (int k = 0; k < 3; ++k) {
             out[3 * k] = out[3 * k + 1] = 0.f;
@@ -308,8 +311,15 @@ __device__ __forceinline__ unsigned shadow_warp_mask(const float4* __restrict__ 
     return __ballot_sync(kFull, keep);
 }
 
+// Besides the sign test, a candidate is dropped when its plane is hit CERTAINLY beyond the occlusion threshold
+// thr = r*0.99f (raytracer.cpp:313) -- typically the triangle the shaded point itself lies on.  With the scaled,
+// sign-normalised denominator Ds = G1+G2+G3 - 3*1.0001 = s*d0/M, the ray parameter of the plane hit is tnum/Ds.
+// Only well-conditioned pairs qualify (Ds >= 2^12, i.e. |d0| >= 2^-6*L1): there the reference's u, v, hit position
+// and distance are within posErr + 2^-13*t of the exact values (derivation in DESIGN.md 3.1), so its computed
+// distance cannot be below thr and the exact test could only say "not an occluder".
 template <bool FILTER>
-__device__ __forceinline__ unsigned shadow_ray_mask(const float4* __restrict__ Fo, int base, unsigned warpMask, V3 r) {
+__device__ __forceinline__ unsigned shadow_ray_mask(const float4* __restrict__ Fo, int base, unsigned warpMask, V3 r,
+                                                    float thr) {
     if (!FILTER) return warpMask;
     unsigned m = 0u;
     for (unsigned tm = warpMask; tm; tm &= tm - 1) {
@@ -319,7 +329,11 @@ __device__ __forceinline__ unsigned shadow_ray_mask(const float4* __restrict__ F
         const float G1 = fmaf(c1.x, r.x, fmaf(c1.y, r.y, fmaf(c1.z, r.z, kShadowMargin)));
         const float G2 = fmaf(c2.x, r.x, fmaf(c2.y, r.y, fmaf(c2.z, r.z, kShadowMargin)));
         const float G3 = fmaf(c3.x, r.x, fmaf(c3.y, r.y, fmaf(c3.z, r.z, kShadowMargin)));
-        if ((int)(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3)) >= 0) m |= 1u << j;
+        if ((int)(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3)) >= 0) {
+            const float Ds = (G1 + G2) + (G3 - 3.0f * kShadowMargin);
+            const bool beyond = Ds >= 4096.0f && fmaf(__fdividef(c1.w, Ds), 0.999755859375f /* 1 - 2^-12 */, -c2.w) > thr;
+            if (!beyond) m |= 1u << j;
+        }
     }
     return m;
 }
@@ -344,9 +358,22 @@ __device__ __forceinline__ void write_pair_constants(const float4* __restrict__ 
     X[1] = make_float4(c.e1b.x, c.e1b.y, c.e1b.z, 0.f);
     if (withForms) {
         float q[9];
-        filter_forms(t.n, c.be2, c.e1b, c.nb, primary, f->R, f->focal, f->primaryDmax, q);
-        F[0] = make_float4(q[0], q[1], q[2], 0.f);
-        F[1] = make_float4(q[3], q[4], q[5], 0.f);
+        double invM;
+        filter_forms(t.n, c.be2, c.e1b, c.nb, primary, f->R, f->focal, f->primaryDmax, q, &invM);
+        // Shadow rays only (see shadow_ray_mask): tnum = |nb|/M so that the ray parameter of the plane hit is
+        // tnum / (scaled s*d0); posErr bounds how far the reference's computed hit distance can fall below that.
+        float tnum = 0.f, posErr = 0.f;
+        if (!primary && invM > 0.0) {
+            const double e1n = fabs((double)t.e1.x) + fabs((double)t.e1.y) + fabs((double)t.e1.z) + fabs((double)t.e2.x) +
+                               fabs((double)t.e2.y) + fabs((double)t.e2.z);
+            const double e0n = fabs((double)t.v0.x) + fabs((double)t.v0.y) + fabs((double)t.v0.z) + fabs((double)og.x) +
+                               fabs((double)og.y) + fabs((double)og.z) + e1n;
+            tnum = (float)(fabs((double)c.nb) * invM);
+            posErr = (float)(e1n * 6.103515625e-5 /* 2^-14 */ + e0n * 9.5367431640625e-7 /* 2^-20 */);
+            if (!isfinite(tnum) || !isfinite(posErr)) tnum = posErr = 0.f;
+        }
+        F[0] = make_float4(q[0], q[1], q[2], tnum);
+        F[1] = make_float4(q[3], q[4], q[5], posErr);
         F[2] = make_float4(q[6], q[7], q[8], 0.f);
     }
 }
@@ -553,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                                 if (TILECULL) wm = shadow_warp_mask<FILTER>(Fo, base, T, lane, qlo, qhi, rb);
                                 else wm = (T - base >= 32) ? kFull : ((1u << (T - base)) - 1u);
                                 if (any && !occluded) {
-                                    unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir);
+                                    unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir, thr);
                                     for (; m; m &= m - 1) {
                                         const int i = base + __ffs(m) - 1;
                                         if constexpr (STATS) cnt.exact++;
