@@ -8,7 +8,7 @@ directory name is not a Python identifier, so import it through
 """
 from . import capi  # noqa: F401
 from .capi import (B2RError, Context, FrameParams, camera_rot_from_yaw, cornell_box,  # noqa: F401
-                   default_frame_params, jitter_table, load_library, orbit_camera, tessellate, write_bmp)
+                   default_frame_params, jitter_table, load_library, load_stl, orbit_camera, tessellate, write_bmp)
 
 
 def __getattr__(name):

@@ -95,7 +95,7 @@ SYMBOLS = [
     "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_scene_cornell_box",
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
     "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
-    "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async",
+    "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async", "b2r_scene_load_stl",
 ]
 
 _lib = None
@@ -152,6 +152,8 @@ def load_library():
     lib.b2r_scene_cornell_box.argtypes = [vp, i32, i32]
     lib.b2r_scene_tessellate.argtypes = [vp, i32, i32, i32, vp, i32]
     lib.b2r_scene_tessellate.restype = C.c_longlong
+    lib.b2r_scene_load_stl.argtypes = [C.c_char_p, vp, C.c_longlong, i32]
+    lib.b2r_scene_load_stl.restype = C.c_longlong
     lib.b2r_camera_rot_from_yaw.argtypes = [C.c_float, C.c_float, fp]
     lib.b2r_orbit_camera.argtypes = [i32, i32, C.c_float, fp, fp]
     lib.b2r_jitter_table.argtypes = [C.c_uint, fp, fp]
@@ -368,6 +370,18 @@ def tessellate(tris15, k):
     out = np.zeros((n, 15), np.float32)
     got = load_library().b2r_scene_tessellate(_ptr(tris15), len(tris15), 60, k, _ptr(out), 60)
     assert got == n, (got, n)
+    return out
+
+
+def load_stl(path):
+    """ASCII STL with the reference loader's semantics (LoadSTL.cpp:17-81): (n,15) float32 triangles."""
+    lib = load_library()
+    n = lib.b2r_scene_load_stl(path.encode(), None, 0, 60)
+    if n < 0:
+        raise B2RError(f"b2r_scene_load_stl -> {n}")
+    out = np.zeros((n, 15), np.float32)
+    got = lib.b2r_scene_load_stl(path.encode(), _ptr(out), n, 60)
+    assert got == n
     return out
 
 

@@ -8,6 +8,7 @@
 // are identical (tests pin the FNV-1a32 fingerprint b715a8a2 from SURVEY.md).
 // Compiled with -ffp-contract=off.
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -118,6 +119,65 @@ long long b2r_scene_tessellate(const void* in, int count, int in_stride, int k, 
                                    P(i, j + 1), col);
             }
     }
+    return n;
+}
+
+// ASCII STL ingestion with the reference loader's exact semantics (rasteriser/Source/LoadSTL.cpp:17-81): every line
+// containing "outer" is followed by three vertex lines, split on single spaces with empty tokens and the word
+// "vertex" dropped, each coordinate (float)atof(token); every triangle gets colour (0.5,0.5,0.5); afterwards all
+// coordinates are multiplied by -0.05f and the normal recomputed like the Triangle ctor.
+long long b2r_scene_load_stl(const char* path, void* out, long long capacity, int stride_bytes) {
+    if (!path || (out && stride_bytes != 60 && stride_bytes != 64)) return B2R_E_INVALID;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) return B2R_E_IO;
+    long long n = 0;
+    char* line = nullptr;
+    size_t cap = 0;
+    const float scale = 0.05f;
+    auto read_vertex = [&](F3* v) -> bool {
+        if (getline(&line, &cap, fp) < 0) return false;
+        float c[3] = {0.f, 0.f, 0.f};
+        int got = 0;
+        for (char* tok = line; *tok && got < 3;) {
+            while (*tok == ' ') ++tok;          // delimiters (getline(ss, tok, ' ') yields empty tokens, which are dropped)
+            if (!*tok || *tok == '\n') break;
+            char* end = tok;
+            while (*end && *end != ' ' && *end != '\n') ++end;
+            const bool isWord = (end - tok == 6) && strncmp(tok, "vertex", 6) == 0;
+            if (!isWord) {
+                char save = *end;
+                *end = 0;
+                c[got++] = (float)atof(tok);
+                *end = save;
+            }
+            tok = end;
+        }
+        *v = {c[0], c[1], c[2]};
+        return true;
+    };
+    while (getline(&line, &cap, fp) >= 0) {
+        if (!strstr(line, "outer")) continue;
+        F3 v[3];
+        bool ok = true;
+        for (int k = 0; k < 3 && ok; ++k) ok = read_vertex(&v[k]);
+        if (!ok) break;
+        if (out) {
+            if (n >= capacity) {
+                free(line);
+                fclose(fp);
+                return B2R_E_CAPACITY;
+            }
+            for (int k = 0; k < 3; ++k) {  // x, z, y each *= -scale (LoadSTL.cpp:61-73)
+                v[k].x *= -scale;
+                v[k].z *= -scale;
+                v[k].y *= -scale;
+            }
+            write_triangle((unsigned char*)out + (size_t)n * stride_bytes, stride_bytes, v[0], v[1], v[2], {0.5f, 0.5f, 0.5f});
+        }
+        ++n;
+    }
+    free(line);
+    fclose(fp);
     return n;
 }
 

@@ -222,6 +222,10 @@ int b2r_scene_cornell_box(void* out, int capacity, int stride_bytes);
  * i+j < k-1, "down" (P(i+1,j),P(i+1,j+1),P(i,j+1)); normals recomputed like the Triangle ctor
  * (TestModel.h:26-31).  out may be NULL to query the count.  Returns the output count. */
 long long b2r_scene_tessellate(const void* in, int count, int in_stride, int k, void* out, int out_stride);
+/* ASCII STL mesh with the reference loader's semantics (rasteriser/Source/LoadSTL.cpp:17-81: vertices after every
+ * "outer" line, (float)atof, all coordinates * -0.05f, colour 0.5, normal recomputed).  out may be NULL to count.
+ * Returns the facet count, or a negative error (B2R_E_IO, B2R_E_CAPACITY). */
+long long b2r_scene_load_stl(const char* path, void* out, long long capacity, int stride_bytes);
 /* cameraRot as Update() builds it from yaw (raytracer.cpp:377-382, rasteriser.cpp:378-383);
  * rot11 is the preset [1][1] element: 1.0f (raytracer.cpp:162) or 1.01f (rasteriser.cpp:115). */
 int b2r_camera_rot_from_yaw(float yaw, float rot11, float* rot9_colmajor);

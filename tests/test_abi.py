@@ -105,3 +105,34 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(d, f)).read()
                 assert "liboracle" not in text and "portbind" not in text and "refbind" not in text, os.path.join(d, f)
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), os.path.join(d, f)
+
+
+def test_stl_loader(pkg, tmp_path):
+    """ASCII STL ingestion on a small mesh of our own, incl. the loader's quirks (tokens split on
+    single spaces, the word 'vertex' dropped, everything scaled by -0.05f)."""
+    p = tmp_path / "m.stl"
+    p.write_text("solid t\n facet normal 0 0 1\n  outer loop\n  vertex 1 2 3\n  vertex  4.5  -6  7e0\n   vertex 8 9 10\n  endloop\n"
+                 " endfacet\n facet normal 0 1 0\n  outer loop\n  vertex 0 0 0\n  vertex 20 0 0\n  vertex 0 0 20\n  endloop\n endfacet\nendsolid\n")
+    t = pkg.load_stl(str(p))
+    assert t.shape == (2, 15)
+    s = np.float32(-0.05)
+    assert np.array_equal(t[0, :9], (np.array([1, 2, 3, 4.5, -6, 7, 8, 9, 10], np.float32) * s))
+    assert np.array_equal(t[:, 12:15], np.full((2, 3), 0.5, np.float32))
+    e1, e2 = t[1, 3:6] - t[1, 0:3], t[1, 6:9] - t[1, 0:3]
+    n = np.cross(e2, e1)
+    assert np.allclose(t[1, 9:12], n / np.linalg.norm(n), atol=1e-6)
+    with pytest.raises(pkg.B2RError):
+        pkg.load_stl(str(tmp_path / "missing.stl"))
+
+
+def test_stl_loader_equals_reference_loader(pkg):
+    """Bit-exact against the reference's own LoadSTL on its enemy1.stl (where the reference is mounted)."""
+    from oracle import refbind
+    ref_dir = "/root/reference/rasteriser"
+    if not os.path.isdir(ref_dir) or not refbind.available("ras", 96, 64):
+        pytest.skip("reference sources / oracle/_ref not available")
+    ra = refbind.RefRasteriser(96, 64)
+    want = ra.load_stl(ref_dir)
+    got = pkg.load_stl(os.path.join(ref_dir, "Source", "enemy1.stl"))
+    assert got.shape == want.shape == (9028, 15)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -160,3 +160,35 @@ def test_dof_with_aa_and_soft_shadows(pkg, oracle):
     want = oracle.rt_draw(tris, fp, w, h)
     assert np.array_equal(surf, oracle.resolve_surface(want["pixelColours"], want["focalDistances"], True, 5))
     ctx.close()
+
+
+def test_stl_mesh_end_to_end(pkg, oracle, tmp_path):
+    """an ASCII STL goes through the loader (reference semantics: scale -0.05, grey) and both paths,
+    with the reference's CUSTOM_MODEL camera (rasteriser.cpp:109)."""
+    rng = np.random.default_rng(12)
+    soup = random_soup(rng, 700, spread=14.0, size=5.0)
+    path = tmp_path / "mesh.stl"
+    with open(path, "w") as f:
+        f.write("solid mesh\n")
+        for t in soup:
+            f.write(" facet normal 0 0 0\n  outer loop\n")
+            for k in range(3):
+                f.write("  vertex %.6g %.6g %.6g\n" % tuple(t[3 * k:3 * k + 3]))
+            f.write("  endloop\n endfacet\n\n")
+        f.write("endsolid\n")
+    tris = pkg.load_stl(str(path))
+    assert tris.shape == (700, 15) and np.abs(tris[:, :9]).max() < 1.5
+    w, h = 200, 150
+    fp = pkg.default_frame_params(1, w, h)
+    fp.set_camera([0, -0.5, -5.0], rot_y(0.0, 1.01), float(h))
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(tris)
+    ctx.set_frame(fp)
+    culled = ctx.ras_cull()
+    assert np.array_equal(culled, oracle.ras_cull(tris, fp, w, h))
+    ras_equal(ctx.ras_draw(), oracle.ras_draw(tris, culled, fp, w, h))
+    fr = pkg.default_frame_params(0, w, h)
+    fr.set_camera([0, -0.5, -5.0], rot_y(0.0), float(h))
+    ctx.set_frame(fr)
+    rt_equal(ctx.rt_draw(), oracle.rt_draw(tris, fr, w, h))
+    ctx.close()
