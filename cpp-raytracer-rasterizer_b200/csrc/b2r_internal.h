@@ -47,7 +47,7 @@ struct DevFrame {
 constexpr int kGeomQuads = 5;
 // Per (ray origin, triangle) record: 5 float4 = 80 bytes.
 //   q0 = (be2.xyz, e1e2b)  q1 = (e1b.xyz, 0)                    (raytracer.cpp:218,226-227,231)
-//   q2..q4 = the three conservative filter forms (see rt_kernels.cu)
+//   q2..q4 = the three conservative filter forms (see rt_trace.cu)
 constexpr int kOriginQuads = 5;
 
 struct RtLaunch {
