@@ -326,7 +326,7 @@ def run_gpu_arm(args, pkg):
 
     if rank == 0:
         extra.update(other_configs(pkg, torch, dev, stream, flush, local))
-        cpu = cpu_reference_sample(pkg, row_step=34, steps=1, warmup=0) if world == 1 and not args.no_cpu else None
+        cpu = cpu_reference_sample(pkg, row_step=4, steps=3, warmup=1) if world == 1 and not args.no_cpu else None
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
