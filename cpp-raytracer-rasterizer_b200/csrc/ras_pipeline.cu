@@ -20,7 +20,7 @@
 // depth test, so it is replayed step by step, never re-associated.
 //
 // Pipeline (v2):
-//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 12 rows
+//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 20 rows
 //                 (the 1M-triangle regime) are finished here: the three edge walks
 //                 update per-row left/right ends kept in shared memory, then every
 //                 on-screen fragment goes to the key buffer with atomicMax.  The only
@@ -100,8 +100,9 @@ __device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, 
 
 
 // ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
-constexpr int kSmallRows = 16;      // triangles up to this many polygon rows never leave the SM
-constexpr int kSmallThreads = 64;
+constexpr int kSmallRows = 20;      // triangles up to this many polygon rows are finished by ras_small
+constexpr int kWindowRows = 8;      // rows whose ends are held in shared memory at a time (one walk per window)
+constexpr int kSmallThreads = 128;
 
 struct RasCounters {
     unsigned nBig, bigRows, bigSamples, err;
@@ -155,7 +156,7 @@ __device__ __forceinline__ EdgeStep edge_begin(const RPixel& a, const RPixel& b)
     return e;
 }
 
-__global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(kSmallThreads, 7) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
                                                                    TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
                                                                    int2* __restrict__ triInfo, SmallRow* __restrict__ rowRec,
                                                                    RasCounters* __restrict__ ctr) {
@@ -217,56 +218,67 @@ __global__ void __launch_bounds__(kSmallThreads) ras_small_kernel(RasLaunch a, u
             nDrawn = 1;
             nRows = (unsigned long long)rows;
             const int r0 = max(0, a.y0 - minY), r1 = min(rows, a.y1 - minY);  // rows of this band (DrawRows :743)
-            for (int r = 0; r < rows; ++r) {  // :694-698
-                LX(r) = INT_MAX;
-                RX(r) = -INT_MAX;
-            }
-            // ComputePolygonRows: edges 0->1, 1->2, 2->0 in order, strict </> so the first edge to
-            // reach an extreme x keeps its attributes (:705-733)
+            // Row ends live in shared memory for kWindowRows rows at a time; a triangle with more rows replays its
+            // edge walks once per window (86 % of config 4's triangles need one window).  The accumulation itself
+            // always runs over every step -- only the stores are windowed -- so the values are unchanged.
+            for (int w0 = 0; w0 < rows; w0 += kWindowRows) {
+                const int w1 = min(rows, w0 + kWindowRows);
+                const int e0 = max(w0, r0), e1 = min(w1, r1);  // rows of this window that are in the band
+                if (e0 >= e1) continue;
+                for (int r = 0; r < w1 - w0; ++r) {  // :694-698
+                    LX(r) = INT_MAX;
+                    RX(r) = -INT_MAX;
+                }
+                // ComputePolygonRows: edges 0->1, 1->2, 2->0 in order, strict </> so the first edge to
+                // reach an extreme x keeps its attributes (:705-733)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int j = (e + 1) % 3;
-                EdgeStep st = edge_begin(v[e], v[j]);
-                int r = v[e].y - minY;
-                for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
-                    const int x = f2i_x86(st.cx);
-                    if (x < LX(r)) {
-                        LX(r) = x;
-                        LZ(r) = st.cz;
-                        LPX(r) = st.cpx;
-                        LPY(r) = st.cpy;
+                for (int e = 0; e < 3; ++e) {
+                    const int j = (e + 1) % 3;
+                    EdgeStep st = edge_begin(v[e], v[j]);
+                    int r = v[e].y - minY - w0;
+                    for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
+                        if ((unsigned)r < (unsigned)(w1 - w0)) {
+                            const int x = f2i_x86(st.cx);
+                            if (x < LX(r)) {
+                                LX(r) = x;
+                                LZ(r) = st.cz;
+                                LPX(r) = st.cpx;
+                                LPY(r) = st.cpy;
+                            }
+                            if (x > RX(r)) {
+                                RX(r) = x;
+                                RZ(r) = st.cz;
+                                RPX(r) = st.cpx;
+                                RPY(r) = st.cpy;
+                            }
+                        }
+                        st.cx = xadd(st.cx, st.sx);
+                        st.cz = xadd(st.cz, st.sz);
+                        st.cpx = xadd(st.cpx, st.spx);
+                        st.cpy = xadd(st.cpy, st.spy);
+                        r += st.sgn;
                     }
-                    if (x > RX(r)) {
-                        RX(r) = x;
-                        RZ(r) = st.cz;
-                        RPX(r) = st.cpx;
-                        RPY(r) = st.cpy;
+                }
+                // DrawRows / DrawLineSDL / Bresenham with dy == 0 (:738-753, :592-612, :639-672)
+                for (int rr = e0; rr < e1; ++rr) {
+                    const int r = rr - w0;
+                    const int lx = LX(r), rx = RX(r), pixels = rx - lx;  // :598
+                    const float lz = LZ(r), rz = RZ(r);
+                    {   // one full 32-byte sector per row, for the shade pass
+                        float4* rec = reinterpret_cast<float4*>(rowRec + small_row_slot((unsigned)i, minY + rr));
+                        rec[0] = make_float4(__int_as_float(lx), __int_as_float(rx), lz, rz);
+                        rec[1] = make_float4(LPX(r), LPY(r), RPX(r), RPY(r));
                     }
-                    st.cx = xadd(st.cx, st.sx);
-                    st.cz = xadd(st.cz, st.sz);
-                    st.cpx = xadd(st.cpx, st.spx);
-                    st.cpy = xadd(st.cpy, st.spy);
-                    r += st.sgn;
+                    const float zstep = xdiv_step(xsub(rz, lz), (float)pixels);  // :648 (constant-depth rows: 0/n)
+                    const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
+                    unsigned long long* keyRow = keys + (size_t)(minY + rr - a.y0) * (size_t)a.W;
+                    for (int q = i0; q < i1; ++q) {
+                        const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
+                        if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
+                            atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i, 0u));
+                    }
+                    if (i1 > i0) nTests += (unsigned long long)(i1 - i0);
                 }
-            }
-            // DrawRows / DrawLineSDL / Bresenham with dy == 0 (:738-753, :592-612, :639-672)
-            for (int r = r0; r < r1; ++r) {
-                const int lx = LX(r), rx = RX(r), pixels = rx - lx;  // :598
-                const float lz = LZ(r), rz = RZ(r);
-                {   // one full 32-byte sector per row, for the shade pass
-                    float4* rec = reinterpret_cast<float4*>(rowRec + small_row_slot((unsigned)i, minY + r));
-                    rec[0] = make_float4(__int_as_float(lx), __int_as_float(rx), lz, rz);
-                    rec[1] = make_float4(LPX(r), LPY(r), RPX(r), RPY(r));
-                }
-                const float zstep = xdiv(xsub(rz, lz), (float)pixels);  // :648
-                const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
-                unsigned long long* keyRow = keys + (size_t)(minY + r - a.y0) * (size_t)a.W;
-                for (int q = i0; q < i1; ++q) {
-                    const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
-                    if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
-                        atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i, 0u));
-                }
-                if (i1 > i0) nTests += (unsigned long long)(i1 - i0);
             }
         }
     }
@@ -453,7 +465,7 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
             lx = r.lx;
             lz = r.lz;
             pixels = r.rx - r.lx;                              // :598
-            zstep = xdiv(xsub(r.rz, r.lz), (float)pixels);     // :648
+            zstep = xdiv_step(xsub(r.rz, r.lz), (float)pixels);  // :648
             i0 = max(0, -lx - 1);                              // :663 x >= 0
             i1 = min(pixels, W - lx - 1);                      //      x <  W
             if (i1 < i0) i1 = i0;
@@ -521,9 +533,10 @@ __device__ __forceinline__ void shade_pixel(const DevFrame* __restrict__ f, cons
     const int pixels = r.rx - r.lx;
     const float fi = (float)(x - r.lx - 1);
     const float fdx = (float)pixels;
-    const float zinv = xadd(r.lz, xmul(xdiv(xsub(r.rz, r.lz), fdx), fi));                    // :648,667
+    const float zinv = xadd(r.lz, xmul(xdiv_step(xsub(r.rz, r.lz), fdx), fi));               // :648,667
     const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
-    const V3 pos3d = xadd3(lp, xscale3(xdivs3(xsub3(rp, lp), fdx), fi));                     // :649,668
+    const V3 dp = xsub3(rp, lp);  // the z difference is exactly 0 (pos3d.z == 1): xdiv_step avoids the division slow path
+    const V3 pos3d = xadd3(lp, xscale3(mk3(xdiv_step(dp.x, fdx), xdiv_step(dp.y, fdx), xdiv_step(dp.z, fdx)), fi));  // :649,668
     depth = zinv;  // == the key's high word
     const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
     V3 P = xdivs3(pos3d, zinv);        // :557
@@ -554,7 +567,7 @@ __device__ __forceinline__ void shade_pixel(const DevFrame* __restrict__ f, cons
 // latency of that dependent load chain, not by bandwidth.
 constexpr int kShadePixels = 2;
 
-__global__ void __launch_bounds__(256) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
+__global__ void __launch_bounds__(256, 5) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
                                                         const int2* __restrict__ triInfo,
                                                         const SmallRow* __restrict__ rowRec,
                                                         const RowRec* __restrict__ rows,
@@ -699,7 +712,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     RasCounters host{};
     const RowRec* rowsPtr = nullptr;
     if (T > 0) {
-        const size_t smem = sizeof(int) * 8 * kSmallRows * kSmallThreads;
+        const size_t smem = sizeof(int) * 8 * kWindowRows * kSmallThreads;
         static bool attrSet = false;
         if (!attrSet) {
             if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
