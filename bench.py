@@ -325,7 +325,7 @@ def run_gpu_arm(args, pkg):
         ctx.shared_free(mine)
 
     if rank == 0:
-        extra.update(other_configs(pkg, torch, dev, stream, flush, local))
+        extra.update(other_configs(pkg, torch, dev, stream, flush, local, cpu=(world == 1 and not args.no_cpu)))
         cpu = cpu_reference_sample(pkg, row_step=4, steps=3, warmup=1) if world == 1 and not args.no_cpu else None
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -355,7 +355,7 @@ def run_gpu_arm(args, pkg):
         dist.destroy_process_group()
 
 
-def other_configs(pkg, torch, dev, stream, flush, local):
+def other_configs(pkg, torch, dev, stream, flush, local, cpu=False):
     """The remaining BASELINE configs, device-timed (reported under extra, not the headline)."""
     out = {}
     tris = pkg.cornell_box()
@@ -388,6 +388,15 @@ def other_configs(pkg, torch, dev, stream, flush, local):
         ctx.resolve_surface_device_async(0, 500, col.data_ptr(), 0, surf.data_ptr())
     ms = avg_ms(f1)
     out["rt_500x500"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "Mrays_per_s": 500000 / ms / 1e3}
+    # the same frame through the host ABI all the way to a BMP on disk (what the reference does on Esc, raytracer.cpp:175)
+    import tempfile as _tf
+    bmp = os.path.join(_tf.gettempdir(), f"b2r_bench_{os.getpid()}.bmp")
+    t0 = time.perf_counter()
+    for _ in range(20):
+        ctx.rt_frame()
+        pkg.write_bmp(bmp, ctx.resolve_bgr8(), 500, 500)
+    out["rt_500x500"]["host_abi_with_bmp_write_frames_per_s"] = 20 / (time.perf_counter() - t0)
+    os.unlink(bmp)
     # config 2: rasteriser 500x500
     ctx.set_frame(pkg.default_frame_params(1, 500, 500))
     ctx.ras_cull()
@@ -421,7 +430,40 @@ def other_configs(pkg, torch, dev, stream, flush, local):
                                           "frac": abytes / ms / 1e6 / peak, "algorithmic_bytes": abytes,
                                           "peak_source": src, "scope": "whole Draw() pipeline, all kernels"}}
     ctx.close()
+    if cpu:
+        out["cpu_reference"] = cpu_reference_other_configs(pkg, big)
     return out
+
+
+def cpu_reference_other_configs(pkg, big):
+    """Draw() of the reference itself (oracle/_ref) for the other configs, on this host: raytracer 500^2 with OpenMP on
+    every thread, rasteriser single-threaded (the reference default, rasteriser.cpp:22; its OpenMP mode races)."""
+    from oracle import refbind
+    res = {"cores": os.cpu_count()}
+    if refbind.available("rt", 500, 500):
+        rt = refbind.RefRaytracer(500, 500)
+        rt.load_test_model()
+        rt.set_lights([[0, -0.5, -0.7, 1, 1, 1, 14]])
+        rt.set_camera_yaw([0, 0, -2], 0.0, 250.0)
+        rt.set_flags(threads=os.cpu_count())
+        rt.time_draw()
+        res["rt_500x500_ms"] = min(rt.time_draw() for _ in range(5)) * 1e3
+    if refbind.available("ras", 500, 500):
+        ra = refbind.RefRasteriser(500, 500)
+        ra.load_test_model()
+        ra.set_lights([[0, -0.5, -0.7, 1, 1, 1, 14]])
+        ra.set_flags()
+        ra.update_yaw([0, 0, -3], 0.0, 500.0)
+        ra.time_draw()
+        res["ras_500x500_ms"] = min(ra.time_draw() for _ in range(5)) * 1e3
+    if refbind.available("ras", W4K, H4K):
+        ra = refbind.RefRasteriser(W4K, H4K)
+        ra.set_triangles(big)
+        ra.set_lights([[0, -0.5, -0.7, 1, 1, 1, 14]])
+        ra.set_flags()
+        ra.update_yaw([0, 0, -3], 0.0, float(H4K))
+        res["ras_4k_1m_tris_ms"] = min(ra.time_draw() for _ in range(2)) * 1e3
+    return res
 
 
 def main():
