@@ -445,6 +445,29 @@ int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float*
     a.culled = c->culled.as<unsigned char>();
     a.T = c->T;
     a.frame = c->frame.as<DevFrame>();
+    {
+        const DevFrame& f = c->hostFrame;
+        RasFrame& r = a.fr;
+        for (int i = 0; i < 3; ++i) {
+            r.cam[i] = f.cam[i];
+            r.reflectance[i] = f.reflectance[i];
+            r.indirect[i] = f.indirect[i];
+        }
+        for (int i = 0; i < 9; ++i) {
+            r.R[i] = f.R[i];
+            r.Rinv[i] = f.Rinv[i];
+        }
+        r.focal = f.focal;
+        r.dofFocal = f.dofFocal;
+        r.halfW = xdiv((float)c->W, 2.0f);
+        r.halfH = xdiv((float)c->H, 2.0f);
+        r.nLights = f.nLights;
+        for (int k = 0; k < B2R_MAX_LIGHTS; ++k)
+            for (int i = 0; i < 3; ++i) {
+                r.lightPos[k][i] = f.lightPos[k][i];
+                r.lightColor[k][i] = f.lightColor[k][i];
+            }
+    }
     a.W = c->W;
     a.H = c->H;
     a.y0 = y0;

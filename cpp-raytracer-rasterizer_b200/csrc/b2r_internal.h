@@ -65,12 +65,25 @@ struct RtLaunch {
     int useFilter;
 };
 
+// Frame constants the rasteriser kernels need, passed by value in the kernel-parameter bank.
+struct RasFrame {
+    float cam[3], focal;
+    float R[9], dofFocal;
+    float Rinv[9];
+    float halfW, halfH;       // SCREEN_WIDTH / 2.0f, SCREEN_HEIGHT / 2.0f (rasteriser.cpp:544-545)
+    int nLights;
+    float reflectance[3], indirect[3];
+    float lightPos[B2R_MAX_LIGHTS][3];
+    float lightColor[B2R_MAX_LIGHTS][3];  // color*intensity (rasteriser.cpp:577)
+};
+
 struct RasLaunch {
     const unsigned char* raw;  // reference Triangle records
     int stride;                // 60 or 64
     const unsigned char* culled;  // one byte per triangle (may be null => nothing culled)
     int T;
     const DevFrame* frame;
+    RasFrame fr;
     int W, H, y0, y1;
     float* depth;
     float* colours;

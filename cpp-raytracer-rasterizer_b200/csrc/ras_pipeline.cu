@@ -86,15 +86,18 @@ struct RowRec {  // 12 words: left/right ends of one polygon row (y implied)
 constexpr int kMaxRowsPerTriangle = 1 << 22;
 constexpr int kCoordLimit = 1 << 24;
 
-__device__ __forceinline__ RPixel vertex_shader(const DevFrame* f, V3 v, int W, int H) {
+// f: frame constants in the kernel-parameter bank (uniform loads, no global traffic per vertex)
+__device__ __forceinline__ RPixel vertex_shader(const RasFrame& f, V3 v) {
     RPixel p;
-    V3 pos = xvec_mat(xsub3(v, mk3(f->cam[0], f->cam[1], f->cam[2])), f->R);  // :535
-    p.p = xdivs3(pos, pos.z);                                                   // :538
+    V3 pos = xvec_mat(xsub3(v, mk3(f.cam[0], f.cam[1], f.cam[2])), f.R);       // :535
+    // :538 pos / pos.z; the z component is x/x == 1.0f exactly for every finite non-zero x
+    const bool plain = pos.z != 0.0f && fabsf(pos.z) <= 3.402823466e+38f;
+    p.p = mk3(xdiv(pos.x, pos.z), xdiv(pos.y, pos.z), plain ? 1.0f : xdiv(pos.z, pos.z));
     p.zinv = xdiv(1.0f, pos.z);                                                 // :541
-    float fx = xmul(f->focal, xmul(pos.x, p.zinv));
-    float fy = xmul(f->focal, xmul(pos.y, p.zinv));
-    p.x = f2i_x86(xadd(__int2float_rn(f2i_x86(fx)), xdiv((float)W, 2.0f)));    // :544
-    p.y = f2i_x86(xadd(__int2float_rn(f2i_x86(fy)), xdiv((float)H, 2.0f)));    // :545
+    float fx = xmul(f.focal, xmul(pos.x, p.zinv));
+    float fy = xmul(f.focal, xmul(pos.y, p.zinv));
+    p.x = f2i_x86(xadd(__int2float_rn(f2i_x86(fx)), f.halfW));                 // :544  + (SCREEN_WIDTH / 2.0f)
+    p.y = f2i_x86(xadd(__int2float_rn(f2i_x86(fy)), f.halfH));                 // :545
     return p;
 }
 
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(kSmallThreads, 7) ras_small_kernel(RasLaunch a
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v[k] = vertex_shader(a.frame, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]), a.W, a.H);  // :760-761
+            v[k] = vertex_shader(a.fr, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]));  // :760-761
             maxY = max(maxY, v[k].y);
             minY = min(minY, v[k].y);
             bad = bad || v[k].x <= -kCoordLimit || v[k].x >= kCoordLimit || v[k].y <= -kCoordLimit || v[k].y >= kCoordLimit;
@@ -527,8 +530,9 @@ __device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long
 }
 
 // PixelShader (:549-589) for the fragment of pixel x on the winner's row.
-__device__ __forceinline__ void shade_pixel(const DevFrame* __restrict__ f, const ShadeIn& in, int x, float& depth,
+__device__ __forceinline__ void shade_pixel(const RasFrame& fr, const ShadeIn& in, int x, float& depth,
                                             float& focal, V3& colour) {
+    const RasFrame* f = &fr;
     const RowRec& r = in.r;
     const int pixels = r.rx - r.lx;
     const float fi = (float)(x - r.lx - 1);
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(256, 5) ras_shade_kernel(RasLaunch a, const Tr
         int winner = -1;
         if (key[p] != 0ull) {
             winner = (int)key_triangle(key[p]);
-            shade_pixel(a.frame, in[p], x, depth, focal, colour);
+            shade_pixel(a.fr, in[p], x, depth, focal, colour);
         }
         const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
         if (a.depth) a.depth[idx] = depth;
