@@ -50,6 +50,7 @@ __device__ __forceinline__ int f2i_x86(float f) {
 // __fdiv_rn's fast path bails out to a ~100-instruction routine for a zero numerator, and a warp pays for it
 // if any lane does; 0/b is +-0 with the XOR of the signs for every finite non-zero or infinite b.
 __device__ __forceinline__ float xdiv_step(float a, float b) {
+    if (b == 1.0f) return a;  // two-row edges: x/1 == x
     if (a == 0.0f && b != 0.0f && b == b)
         return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000);
     return xdiv(a, b);
@@ -241,7 +242,9 @@ __global__ void __launch_bounds__(kSmallThreads, 7) ras_small_kernel(RasLaunch a
                     int r = v[e].y - minY - w0;
                     for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
                         if ((unsigned)r < (unsigned)(w1 - w0)) {
-                            const int x = f2i_x86(st.cx);
+                            // int(current.x): the chain stays within one pixel of the vertex range, which passed
+                            // the +-2^24 limit, so the plain truncating conversion equals the x86 one
+                            const int x = __float2int_rz(st.cx);
                             if (x < LX(r)) {
                                 LX(r) = x;
                                 LZ(r) = st.cz;
