@@ -45,10 +45,8 @@ struct DevFrame {
 //   q3 = (nh.x, nh.y, nh.z, col.r)  nh = normalize(normal)      (raytracer.cpp:300)
 //   q4 = (col.g, col.b, 0, 0)
 constexpr int kGeomQuads = 5;
-// Per (ray origin, triangle) record: 5 float4 = 80 bytes.
-//   q0 = (be2.xyz, e1e2b)  q1 = (e1b.xyz, 0)                    (raytracer.cpp:218,226-227,231)
-//   q2..q4 = the three conservative filter forms (see rt_trace.cu)
-constexpr int kOriginQuads = 5;
+// Per (ray origin, triangle): 2 float4 of exact constants  (be2.xyz, e1e2b), (e1b.xyz, 0)
+// (raytracer.cpp:218,226-227,231) and 3 float4 of conservative filter forms (see rt_trace.cu).
 
 struct RtLaunch {
     const float4* geom;      // T * kGeomQuads
@@ -167,7 +165,6 @@ struct Ctx {
 
     DevBuf stats;
     bool statsOn = false;
-    unsigned long long hostStats[B2R_STAT_COUNT] = {0};
     unsigned long long launches = 0;
     int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0;
     int lastDraw = -1;  // 0 raytracer, 1 rasteriser

@@ -275,15 +275,16 @@ __global__ void __launch_bounds__(kSmallThreads, 7) ras_small_kernel(RasLaunch a
                         rec[0] = make_float4(__int_as_float(lx), __int_as_float(rx), lz, rz);
                         rec[1] = make_float4(LPX(r), LPY(r), RPX(r), RPY(r));
                     }
-                    const float zstep = xdiv_step(xsub(rz, lz), (float)pixels);  // :648 (constant-depth rows: 0/n)
                     const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
+                    if (i1 <= i0) continue;  // no fragment (incl. pixels == 0, whose 0/0 step nobody reads)
+                    const float zstep = xdiv_step(xsub(rz, lz), (float)pixels);  // :648 (constant-depth rows: 0/n)
                     unsigned long long* keyRow = keys + (size_t)(minY + rr - a.y0) * (size_t)a.W;
                     for (int q = i0; q < i1; ++q) {
                         const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
                         if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
                             atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i, 0u));
                     }
-                    if (i1 > i0) nTests += (unsigned long long)(i1 - i0);
+                    nTests += (unsigned long long)(i1 - i0);
                 }
             }
         }
@@ -471,10 +472,10 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
             lx = r.lx;
             lz = r.lz;
             pixels = r.rx - r.lx;                              // :598
-            zstep = xdiv_step(xsub(r.rz, r.lz), (float)pixels);  // :648
             i0 = max(0, -lx - 1);                              // :663 x >= 0
             i1 = min(pixels, W - lx - 1);                      //      x <  W
             if (i1 < i0) i1 = i0;
+            if (i1 > i0) zstep = xdiv_step(xsub(r.rz, r.lz), (float)pixels);  // :648
         }
     }
     const int count = i1 - i0;
