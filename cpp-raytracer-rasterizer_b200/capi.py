@@ -18,6 +18,8 @@ RANDOM_POSITIONS = 256
 INTERSECTION_DTYPE = np.dtype(
     [("position", np.float32, 3), ("distance", np.float32), ("triangleIndex", np.int32)])
 assert INTERSECTION_DTYPE.itemsize == 20
+PIXEL_DTYPE = np.dtype([("x", np.int32), ("y", np.int32), ("zinv", np.float32), ("pos3d", np.float32, 3)])
+assert PIXEL_DTYPE.itemsize == 24
 
 
 class Light(C.Structure):
@@ -96,6 +98,8 @@ SYMBOLS = [
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
     "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
     "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async", "b2r_scene_load_stl",
+    "b2r_rt_closest_intersection_batch", "b2r_rt_direct_light_batch", "b2r_ras_vertex_shader_batch",
+    "b2r_ras_interpolate", "b2r_ras_compute_polygon_rows", "b2r_ras_pixel_shader_batch",
 ]
 
 _lib = None
@@ -143,6 +147,12 @@ def load_library():
     lib.b2r_shared_close.argtypes = [vp, vp]
     lib.b2r_copy_device_async.argtypes = [vp, vp, vp, C.c_size_t]
     lib.b2r_resolve_surface_multi_device_async.argtypes = [vp, i32, i32, vp, vp, C.POINTER(vp), i32]
+    lib.b2r_rt_closest_intersection_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.b2r_rt_direct_light_batch.argtypes = [vp, i32, vp, vp]
+    lib.b2r_ras_vertex_shader_batch.argtypes = [vp, i32, vp, vp]
+    lib.b2r_ras_interpolate.argtypes = [vp, vp, vp, i32, vp]
+    lib.b2r_ras_compute_polygon_rows.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
+    lib.b2r_ras_pixel_shader_batch.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.b2r_launch_count.argtypes = [vp]
     lib.b2r_launch_count.restype = C.c_ulonglong
     lib.b2r_get_stats.argtypes = [vp, C.POINTER(C.c_ulonglong)]
@@ -330,6 +340,61 @@ class Context:
         arr = (C.c_void_p * len(d_surfaces))(*d_surfaces)
         self._chk(self.lib.b2r_resolve_surface_multi_device_async(self.handle, y0, y1, C.c_void_p(d_colours),
                                                                   C.c_void_p(d_focal), arr, len(d_surfaces)))
+
+    # sub-stage entry points (the reference's callee functions, batched) ---------------------------
+    def closest_intersection(self, starts, dirs, closest=None, is_light=None):
+        starts = np.ascontiguousarray(starts, np.float32).reshape(-1, 3)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        n = len(starts)
+        io = np.zeros(n, INTERSECTION_DTYPE)
+        if closest is None:
+            io["distance"] = np.finfo(np.float32).max
+            io["triangleIndex"] = -1
+        else:
+            io[:] = closest
+        il = None if is_light is None else np.ascontiguousarray(is_light, np.int32)
+        hit = np.zeros(n, np.int32)
+        foc = np.zeros(n, np.float32)
+        self._chk(self.lib.b2r_rt_closest_intersection_batch(self.handle, n, _ptr(starts), _ptr(dirs), _ptr(il), _ptr(io),
+                                                             _ptr(hit), _ptr(foc)))
+        return hit.astype(bool), io, foc
+
+    def direct_light(self, hits):
+        h = np.ascontiguousarray(hits, INTERSECTION_DTYPE).reshape(-1)
+        out = np.zeros((len(h), 3), np.float32)
+        self._chk(self.lib.b2r_rt_direct_light_batch(self.handle, len(h), _ptr(h), _ptr(out)))
+        return out
+
+    def vertex_shader(self, verts):
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+        out = np.zeros(len(v), PIXEL_DTYPE)
+        self._chk(self.lib.b2r_ras_vertex_shader_batch(self.handle, len(v), _ptr(v), _ptr(out)))
+        return out
+
+    def interpolate(self, a, b, n):
+        a = np.atleast_1d(np.array(a, PIXEL_DTYPE))
+        b = np.atleast_1d(np.array(b, PIXEL_DTYPE))
+        out = np.zeros(n, PIXEL_DTYPE)
+        self._chk(self.lib.b2r_ras_interpolate(self.handle, _ptr(a), _ptr(b), n, _ptr(out)))
+        return out
+
+    def compute_polygon_rows(self, vertex_pixels, max_rows=8192):
+        vp = np.ascontiguousarray(vertex_pixels, PIXEL_DTYPE)
+        left = np.zeros(max_rows, PIXEL_DTYPE)
+        right = np.zeros(max_rows, PIXEL_DTYPE)
+        rows = C.c_int(0)
+        self._chk(self.lib.b2r_ras_compute_polygon_rows(self.handle, _ptr(vp), _ptr(left), _ptr(right), max_rows,
+                                                        C.byref(rows)))
+        return left[:rows.value].copy(), right[:rows.value].copy()
+
+    def pixel_shader(self, pixels, colors, normals):
+        p = np.ascontiguousarray(pixels, PIXEL_DTYPE).reshape(-1)
+        col = np.ascontiguousarray(colors, np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        out = np.zeros((len(p), 3), np.float32)
+        foc = np.zeros(len(p), np.float32)
+        self._chk(self.lib.b2r_ras_pixel_shader_batch(self.handle, len(p), _ptr(p), _ptr(col), _ptr(nrm), _ptr(out), _ptr(foc)))
+        return out, foc
 
     def measure_fp32_peak(self):
         t, s = C.c_double(), C.c_double()

@@ -155,7 +155,7 @@ int b2r_destroy(b2r_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
-                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->stats};
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->subScratch, &c->stats};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);

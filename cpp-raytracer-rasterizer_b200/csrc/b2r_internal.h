@@ -156,6 +156,7 @@ struct Ctx {
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
+    DevBuf subScratch;  // staging of the sub-stage entry points
     DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
     size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
     void* rasKeysCleanPtr = nullptr;

@@ -37,30 +37,9 @@
 
 #include "b2r_internal.h"
 #include "exact.cuh"
+#include "ras_device.cuh"
 
 namespace b2r {
-
-// (int)float with x86 cvttss2si semantics (out of range / NaN -> INT_MIN), which is
-// what the reference's int(...) conversions do on the CPU it was built for.
-__device__ __forceinline__ int f2i_x86(float f) {
-    return (f >= -2147483648.0f && f < 2147483648.0f) ? __float2int_rz(f) : INT_MIN;
-}
-
-// IEEE a/b for the edge-step set-up, where a is very often exactly 0 (axis-aligned edges of a regular mesh).
-// __fdiv_rn's fast path bails out to a ~100-instruction routine for a zero numerator, and a warp pays for it
-// if any lane does; 0/b is +-0 with the XOR of the signs for every finite non-zero or infinite b.
-__device__ __forceinline__ float xdiv_step(float a, float b) {
-    if (b == 1.0f) return a;  // two-row edges: x/1 == x
-    if (a == 0.0f && b != 0.0f && b == b)
-        return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000);
-    return xdiv(a, b);
-}
-
-struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
-    int x, y;
-    float zinv;
-    V3 p;
-};
 
 struct TriSetup {  // 24 words
     int vx[3], vy[3];
@@ -86,22 +65,6 @@ struct RowRec {  // 12 words: left/right ends of one polygon row (y implied)
 
 constexpr int kMaxRowsPerTriangle = 1 << 22;
 constexpr int kCoordLimit = 1 << 24;
-
-// f: frame constants in the kernel-parameter bank (uniform loads, no global traffic per vertex)
-__device__ __forceinline__ RPixel vertex_shader(const RasFrame& f, V3 v) {
-    RPixel p;
-    V3 pos = xvec_mat(xsub3(v, mk3(f.cam[0], f.cam[1], f.cam[2])), f.R);       // :535
-    // :538 pos / pos.z; the z component is x/x == 1.0f exactly for every finite non-zero x
-    const bool plain = pos.z != 0.0f && fabsf(pos.z) <= 3.402823466e+38f;
-    p.p = mk3(xdiv(pos.x, pos.z), xdiv(pos.y, pos.z), plain ? 1.0f : xdiv(pos.z, pos.z));
-    p.zinv = xdiv(1.0f, pos.z);                                                 // :541
-    float fx = xmul(f.focal, xmul(pos.x, p.zinv));
-    float fy = xmul(f.focal, xmul(pos.y, p.zinv));
-    p.x = f2i_x86(xadd(__int2float_rn(f2i_x86(fx)), f.halfW));                 // :544  + (SCREEN_WIDTH / 2.0f)
-    p.y = f2i_x86(xadd(__int2float_rn(f2i_x86(fy)), f.halfH));                 // :545
-    return p;
-}
-
 
 // ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
 constexpr int kSmallRows = 20;      // triangles up to this many polygon rows are finished by ras_small
@@ -536,7 +499,6 @@ __device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long
 // PixelShader (:549-589) for the fragment of pixel x on the winner's row.
 __device__ __forceinline__ void shade_pixel(const RasFrame& fr, const ShadeIn& in, int x, float& depth,
                                             float& focal, V3& colour) {
-    const RasFrame* f = &fr;
     const RowRec& r = in.r;
     const int pixels = r.rx - r.lx;
     const float fi = (float)(x - r.lx - 1);
@@ -546,28 +508,7 @@ __device__ __forceinline__ void shade_pixel(const RasFrame& fr, const ShadeIn& i
     const V3 dp = xsub3(rp, lp);  // the z difference is exactly 0 (pos3d.z == 1): xdiv_step avoids the division slow path
     const V3 pos3d = xadd3(lp, xscale3(mk3(xdiv_step(dp.x, fdx), xdiv_step(dp.y, fdx), xdiv_step(dp.z, fdx)), fi));  // :649,668
     depth = zinv;  // == the key's high word
-    const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
-    V3 P = xdivs3(pos3d, zinv);        // :557
-    P = xvec_mat(P, f->Rinv);          // :559
-    P = xadd3(P, cam);                 // :560
-    const V3 dc = xsub3(cam, P);       // glm::distance(pPos3d, cameraPos) = length(cameraPos - pPos3d)
-    focal = xsub(xsqrt(xdot3(dc, dc)), f->dofFocal);  // :564-565
-    V3 result = mk3(0.f, 0.f, 0.f);
-    for (int k = 0; k < f->nLights; ++k) {  // :567-584
-        const V3 L = mk3(f->lightPos[k][0], f->lightPos[k][1], f->lightPos[k][2]);
-        const V3 dl = xsub3(L, P);
-        const float r2 = xdot3(dl, dl);
-        const float rr = xsqrt(r2);                        // :575
-        const float A = sphere_area(rr);                   // :576
-        const V3 lc = mk3(f->lightColor[k][0], f->lightColor[k][1], f->lightColor[k][2]);  // :577
-        const V3 rDir = xscale3(dl, xdiv(1.0f, rr));       // :578
-        const V3 B = xdivs3_shared(lc, A);                 // :580
-        const V3 D = xscale3(B, std_max(xdot3(rDir, in.normal), 0.0f));  // :582 (normal not re-normalised)
-        result = xadd3(result, D);
-    }
-    const V3 refl = mk3(f->reflectance[0], f->reflectance[1], f->reflectance[2]);
-    const V3 ind = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
-    colour = xmul3(xmul3(refl, xadd3(result, ind)), in.color);  // :587
+    pixel_shader_core(fr, zinv, pos3d, in.normal, in.color, focal, colour);
 }
 
 // kShadePixels pixels per thread (256 apart in x, so every access stays coalesced): the key loads of all of them

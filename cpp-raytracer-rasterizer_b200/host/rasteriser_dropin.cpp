@@ -151,6 +151,61 @@ void Draw() {
                          focalDistances.data(), nullptr);
 }
 
+namespace {
+int push_frame() {
+    if (!g_ctx) return B2R_E_NO_SCENE;
+    b2r_frame_params p;
+    fill_params(p);
+    return b2r_set_frame(g_ctx, &p);
+}
+}  // namespace
+
+void VertexShader(const Vertex& v, Pixel& p) {
+    if ((g_rc = push_frame()) != 0) return;
+    g_rc = b2r_ras_vertex_shader_batch(g_ctx, 1, &v.position.x, &p);
+}
+
+void Interpolate(Pixel a, Pixel b, std::vector<Pixel>& result) {
+    if (!g_ctx) {
+        g_rc = B2R_E_NO_SCENE;
+        return;
+    }
+    g_rc = b2r_ras_interpolate(g_ctx, &a, &b, (int)result.size(), result.data());
+}
+
+void ComputePolygonRows(const std::vector<Pixel>& vertexPixels, std::vector<Pixel>& leftPixels,
+                        std::vector<Pixel>& rightPixels) {
+    if (!g_ctx || vertexPixels.size() < 3) {
+        g_rc = B2R_E_NO_SCENE;
+        return;
+    }
+    int maxY = vertexPixels[0].y, minY = vertexPixels[0].y;
+    for (int k = 1; k < 3; ++k) {
+        if (vertexPixels[k].y > maxY) maxY = vertexPixels[k].y;
+        if (vertexPixels[k].y < minY) minY = vertexPixels[k].y;
+    }
+    const long long rows = (long long)maxY - minY + 1;  // :682
+    if (rows > (1 << 22)) {
+        g_rc = B2R_E_CAPACITY;
+        return;
+    }
+    leftPixels.resize((size_t)rows);   // :687-688
+    rightPixels.resize((size_t)rows);
+    int got = 0;
+    g_rc = b2r_ras_compute_polygon_rows(g_ctx, vertexPixels.data(), leftPixels.data(), rightPixels.data(), (int)rows, &got);
+}
+
+void PixelShader(const Pixel& p, vec3 color, vec3 normal) {
+    if ((g_rc = push_frame()) != 0) return;
+    vec3 out(0, 0, 0);
+    float focal = 0.0f;
+    g_rc = b2r_ras_pixel_shader_batch(g_ctx, 1, &p, &color.x, &normal.x, &out.x, &focal);
+    if (g_rc == 0 && p.x >= 0 && p.y >= 0 && p.x < SCREEN_WIDTH && p.y < SCREEN_HEIGHT) {
+        focalDistances[(size_t)p.y * SCREEN_WIDTH + p.x] = focal;   // :565
+        pixelColours[(size_t)p.y * SCREEN_WIDTH + p.x] = out;       // :588
+    }
+}
+
 int SaveBMP(const char* path) {
     if (!g_ctx) return B2R_E_NO_SCENE;
     std::vector<uint8_t> bgr(b2r_bmp_payload_bytes(SCREEN_WIDTH, SCREEN_HEIGHT));

@@ -43,6 +43,13 @@ void AddLight(vec3 position, vec3 color, float intensity);    // :158-165
 void DeleteLight();                                           // :168-172
 void Update();   // :174-449 without SDL
 void Draw();     // :461-482 -- the hot path, on the GPU
+// The stages Draw() is made of, with the reference's signatures (rasteriser.cpp:532,549,615,674); each call runs
+// that stage on the GPU for the current globals (one item per call: for testing and porting, not for speed).
+void VertexShader(const Vertex& v, Pixel& p);                                               // :532-546
+void Interpolate(Pixel a, Pixel b, std::vector<Pixel>& result);                             // :615-637
+void ComputePolygonRows(const std::vector<Pixel>& vertexPixels, std::vector<Pixel>& leftPixels,
+                        std::vector<Pixel>& rightPixels);                                   // :674-735
+void PixelShader(const Pixel& p, vec3 color, vec3 normal);                                  // :549-589
 int SaveBMP(const char* path);
 const char* LastError();
 }  // namespace raref

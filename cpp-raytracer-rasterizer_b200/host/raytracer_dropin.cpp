@@ -109,17 +109,15 @@ void Update() {
     cameraRot[2][2] = c;
 }
 
-void Draw() {
-    if (!g_ctx) {
-        g_rc = B2R_E_NO_SCENE;
-        return;
-    }
-    // the scene is (re)uploaded only when the global vector changed
-    if (g_uploaded != triangles.data() || g_uploadedCount != triangles.size()) {
-        g_rc = b2r_set_triangles(g_ctx, triangles.data(), (int)triangles.size(), (int)sizeof(Triangle));
-        if (g_rc) return;
-        g_uploaded = triangles.data();
-        g_uploadedCount = triangles.size();
+namespace {
+// scene + frame globals -> device; the scene is (re)uploaded only when the vector changed
+int push_state(const std::vector<Triangle>& tris) {
+    if (!g_ctx) return B2R_E_NO_SCENE;
+    if (g_uploaded != tris.data() || g_uploadedCount != tris.size()) {
+        int rc = b2r_set_triangles(g_ctx, tris.data(), (int)tris.size(), (int)sizeof(Triangle));
+        if (rc) return rc;
+        g_uploaded = tris.data();
+        g_uploadedCount = tris.size();
     }
     b2r_frame_params p;
     std::memset(&p, 0, sizeof p);
@@ -138,9 +136,34 @@ void Draw() {
     p.dofEnabled = DOF_ENABLED;
     p.dofKernelSize = DOF_KERNEL_SIZE;
     p.currentReflectance[0] = p.currentReflectance[1] = p.currentReflectance[2] = 1.0f;
-    if ((g_rc = b2r_set_frame(g_ctx, &p)) != 0) return;
+    return b2r_set_frame(g_ctx, &p);
+}
+}  // namespace
+
+void Draw() {
+    if ((g_rc = push_state(triangles)) != 0) return;
     g_rc = b2r_rt_frame(g_ctx, screenPixels.data(), reinterpret_cast<float*>(pixelColours.data()),
                         reinterpret_cast<b2r_intersection*>(closestIntersections.data()), focalDistances.data());
+}
+
+bool ClosestIntersection(vec3 start, vec3 dir, const std::vector<Triangle>& tris, Intersection& closestIntersection,
+                         bool isLight, int x, int y) {
+    if ((g_rc = push_state(tris)) != 0) return false;
+    int32_t light = isLight ? 1 : 0, hit = 0;
+    float focal = 0.0f;
+    g_rc = b2r_rt_closest_intersection_batch(g_ctx, 1, &start.x, &dir.x, &light,
+                                             reinterpret_cast<b2r_intersection*>(&closestIntersection), &hit, &focal);
+    // :248-249: the primary-ray call also records the focal distance of an updated hit
+    if (g_rc == 0 && !isLight && focal != 0.0f && x >= 0 && y >= 0 && x < SCREEN_WIDTH && y < SCREEN_HEIGHT)
+        focalDistances[(size_t)y * SCREEN_WIDTH + x] = focal;
+    return g_rc == 0 && hit != 0;
+}
+
+vec3 DirectLight(const Intersection& i) {
+    vec3 out(0, 0, 0);
+    if ((g_rc = push_state(triangles)) != 0) return out;
+    g_rc = b2r_rt_direct_light_batch(g_ctx, 1, reinterpret_cast<const b2r_intersection*>(&i), &out.x);
+    return out;
 }
 
 int SaveBMP(const char* path) {

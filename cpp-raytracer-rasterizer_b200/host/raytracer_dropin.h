@@ -47,6 +47,11 @@ void AddLight(vec3 position, vec3 color, float intensity);    // :180-193 (jitte
 void DeleteLight();                                           // :195-199
 void Update();   // :329-545 without SDL: the per-frame reset (:335-339, done on the GPU) and cameraRot from yaw (:377-382)
 void Draw();     // :547-606 -- the hot path, on the GPU; fills pixelColours/focalDistances/closestIntersections/screenPixels
+// The stages Draw() is made of, with the reference's signatures (raytracer.cpp:105-107); each call runs that
+// stage on the GPU for the current globals (one item per call: for testing and porting, not for speed).
+bool ClosestIntersection(vec3 start, vec3 dir, const std::vector<Triangle>& triangles,
+                         Intersection& closestIntersection, bool isLight, int x, int y);   // :202-257
+vec3 DirectLight(const Intersection& i);                                                   // :265-327
 int SaveBMP(const char* path);                                // SDL_SaveBMP(screen, path), :175
 const char* LastError();
 }  // namespace rtref

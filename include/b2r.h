@@ -212,6 +212,29 @@ int b2r_copy_device_async(b2r_ctx* ctx, void* d_dst, const void* d_src, size_t b
 int b2r_resolve_surface_multi_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_pixelColours,
                                            const float* d_focalDistances, uint32_t* const* d_surfaces, int n);
 
+/* ---- sub-stage entry points ------------------------------------------------------------------------- */
+/* The reference's callee functions (raytracer.cpp:105-107, rasteriser.cpp:87-94) on caller-provided inputs:
+ * batched, host pointers, synchronous; each runs exactly that stage in reference-order arithmetic with the current
+ * scene (b2r_set_triangles) and frame params (b2r_set_frame).  Pixel = the reference's 24-byte struct
+ * {int x, y; float zinv; vec3 pos3d} (rasteriser TestModel.h:34-53).
+ *   ClosestIntersection(start, dir, triangles, closest&, isLight, x, y) -> bool   raytracer.cpp:202-257
+ *       io[k] is the running closest intersection (in/out); hit[k] the return value; focal[k] the value the call
+ *       would store in focalDistances (0 if it stored none); isLight may be NULL (all false).
+ *   DirectLight(const Intersection&) -> vec3                                       raytracer.cpp:265-327
+ *   VertexShader(const Vertex&, Pixel&)                                            rasteriser.cpp:532-546
+ *   Interpolate(Pixel a, Pixel b, vector<Pixel>& result)  (result.size() == n)     rasteriser.cpp:615-637
+ *   ComputePolygonRows(vertexPixels[3], left&, right&)    (*rows = ROWS)           rasteriser.cpp:674-735
+ *   PixelShader(const Pixel&, color, normal)  -> the pixelColours / focalDistances values it would store  :549-589 */
+int b2r_rt_closest_intersection_batch(b2r_ctx* ctx, int n, const float* starts3, const float* dirs3,
+                                      const int32_t* isLight, b2r_intersection* io, int32_t* hit, float* focal);
+int b2r_rt_direct_light_batch(b2r_ctx* ctx, int n, const b2r_intersection* hits, float* out3);
+int b2r_ras_vertex_shader_batch(b2r_ctx* ctx, int n, const float* verts3, void* pixels24);
+int b2r_ras_interpolate(b2r_ctx* ctx, const void* a24, const void* b24, int n, void* out24);
+int b2r_ras_compute_polygon_rows(b2r_ctx* ctx, const void* vertexPixels3x24, void* left24, void* right24, int maxRows,
+                                 int* rows);
+int b2r_ras_pixel_shader_batch(b2r_ctx* ctx, int n, const void* pixels24, const float* colors3, const float* normals3,
+                               float* outColours3, float* outFocal);
+
 /* ---- host-side scene helpers (no GPU involved) ---------------------------- */
 /* LoadTestModel (raytracer TestModel.h:51-192 == rasteriser TestModel.h:151-292): the 30-triangle
  * Cornell box, written as reference Triangle records of the given stride (60 or 64).  Returns the

@@ -60,3 +60,13 @@ def test_headless_orbit_animation(tmp_path):
     subprocess.check_call([os.path.join(LIBDIR, "b2r_headless"), "raytracer", "96", "64", "--frames", "4", "--out", out])
     frames = [open(f"{out}_{i:04d}.bmp", "rb").read() for i in range(4)]
     assert len(set(frames)) == 4
+
+
+@pytest.mark.gpu
+def test_stage_functions_reassemble_draw():
+    """host/stage_check.cpp: the reference's Draw() loops rebuilt from ClosestIntersection/DirectLight and
+    VertexShader/ComputePolygonRows/PixelShader (reference signatures, GPU-backed) equal the fused Draw() bit for bit."""
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    out = subprocess.run([os.path.join(LIBDIR, "b2r_stage_check")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "raytracer stages vs Draw(): 0 of" in out.stdout and "rasteriser stages vs Draw(): 0 of" in out.stdout
