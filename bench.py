@@ -283,6 +283,32 @@ def run_gpu_arm(args, pkg):
     extra = {"frames_per_s": world * args.steps / (total_ms * 1e-3), "rays_per_frame": rays,
              "algorithmic_gflop_per_frame": flops / 1e9, "e2e_frames_per_s": world * args.steps / e2e_s}
 
+    # BASELINE config 5: 360-frame camera orbit, frames partitioned across the ranks (no collective on the data path);
+    # every frame re-uploads its camera (b2r_set_frame) and is traced + resolved at 4K, 1 spp + hard shadow
+    par = pkg.parallel
+    fp_orbit = pkg.default_frame_params(0, W4K, H4K)
+    my_frames = par.frames_for_rank(rank, world, 360)
+    def orbit_pass():
+        for fidx in my_frames:
+            pos, rot = pkg.orbit_camera(fidx, 360)
+            fp_orbit.set_camera(pos, rot, H4K / 2)
+            ctx.set_frame(fp_orbit)
+            ctx.rt_draw_device_async(0, H4K, d_col.data_ptr())
+            ctx.resolve_surface_device_async(0, H4K, d_col.data_ptr(), 0, d_surf.data_ptr())
+    orbit_pass()  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    orbit_pass()
+    barrier()
+    orbit_s = time.perf_counter() - t0
+    t = torch.tensor([orbit_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    orbit_s = float(t.item())
+    extra["orbit_360_frames_4k_1spp"] = {"seconds": orbit_s, "frames_per_s": 360 / orbit_s,
+                                         "partition": f"frames f = rank (mod {world})", "timing": "wall clock incl. per-frame b2r_set_frame"}
+    ctx.set_frame(fp)
+
     # single-frame row-band split + NCCL all-gather of the surface bands (strong scaling, N > 1 only)
     if world > 1 and H4K % world == 0:
         band = H4K // world
