@@ -139,7 +139,7 @@ int b2r_create(b2r_ctx** out, int device, int width, int height) {
         return cuda_fail(nullptr, e, "cudaStreamCreate");
     }
     c->stream = c->ownStream;
-    if ((e = cudaMallocHost((void**)&c->pinnedFrame, sizeof(DevFrame))) != cudaSuccess ||
+    if ((e = cudaMallocHost((void**)&c->pinnedFrame, sizeof(DevFrame) * kFrameRing)) != cudaSuccess ||
         (e = cudaMallocHost(&c->pinned, 4096)) != cudaSuccess || (e = c->frame.reserve(sizeof(DevFrame))) != cudaSuccess) {
         b2r_destroy(reinterpret_cast<b2r_ctx*>(c));
         return cuda_fail(nullptr, e, "b2r_create: allocation");
@@ -159,6 +159,8 @@ int b2r_destroy(b2r_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
+    for (int i = 0; i < kFrameRing; ++i)
+        if (c->frameUploaded[i]) cudaEventDestroy(c->frameUploaded[i]);
     if (c->copyStream) {
         cudaStreamDestroy(c->copyStream);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(c->partDone[i]);
@@ -283,10 +285,17 @@ int b2r_set_frame(b2r_ctx* ctx, const b2r_frame_params* p) {
         }
     }
     c->params = *p;
-    CU(cudaStreamSynchronize(c->stream), "sync before frame upload");  // pinnedFrame may still be in flight
-    memcpy(c->pinnedFrame, &f, sizeof f);
+    // pinned staging ring: a slot is reused only after its own upload has completed, so consecutive frames never
+    // wait for the GPU (the copy into c->frame is stream-ordered after the kernels that still read the old frame)
+    const int slot = c->frameSlot;
+    c->frameSlot = (slot + 1) % kFrameRing;
+    if (c->frameUploaded[slot]) CU(cudaEventSynchronize(c->frameUploaded[slot]), "wait for the staging slot");
+    else CU(cudaEventCreateWithFlags(&c->frameUploaded[slot], cudaEventDisableTiming), "cudaEventCreate");
+    DevFrame* stage = c->pinnedFrame + slot;
+    memcpy(stage, &f, sizeof f);
     const size_t used = offsetof(DevFrame, origin) + sizeof(float) * 4 * (size_t)f.nOrigins;
-    CU(cudaMemcpyAsync(c->frame.p, c->pinnedFrame, used, cudaMemcpyHostToDevice, c->stream), "frame upload");
+    CU(cudaMemcpyAsync(c->frame.p, stage, used, cudaMemcpyHostToDevice, c->stream), "frame upload");
+    CU(cudaEventRecord(c->frameUploaded[slot], c->stream), "cudaEventRecord");
     c->haveFrame = true;
     return B2R_OK;
 }

@@ -91,6 +91,7 @@ struct RasLaunch {
 };
 
 struct Ctx;
+constexpr int kFrameRing = 8;
 
 // kernels (each returns cudaGetLastError() of its launches)
 cudaError_t launch_tri_prep(Ctx* c, cudaStream_t s);
@@ -148,7 +149,9 @@ struct Ctx {
     // frame
     b2r_frame_params params{};
     DevFrame hostFrame{};
-    DevFrame* pinnedFrame = nullptr;
+    DevFrame* pinnedFrame = nullptr;      // kFrameRing pinned staging slots
+    cudaEvent_t frameUploaded[8] = {};
+    int frameSlot = 0;
     DevBuf frame;
     bool haveFrame = false;
 
