@@ -331,41 +331,46 @@ __global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __r
 }
 
 // ---- stage 2: Interpolate (:615-637), one thread per (triangle, edge) --------
+// One thread per (triangle, edge, chain): the five accumulation chains of an edge (x, zinv, pos3d.xyz) are
+// independent of each other, so each runs its own serial loop -- 15 threads per triangle instead of 3 -- and writes
+// its field of every sample.  A 2160-row edge is latency-bound: one dependent FADD per step and thread.
 __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* listed large triangles */, EdgeSample* __restrict__ samples,
                                  unsigned* __restrict__ rowOwner) {
-    int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = gid / 3, e = gid - 3 * i;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = gid / 15, rem = gid - 15 * i, e = rem / 5, ch = rem - 5 * e;
     if (i >= T) return;
     const TriSetup s = ts[i];
     if (!s.drawn) return;
-    if (e == 0)
-        for (int r = 0; r < s.rows; ++r) rowOwner[s.rowBase + r] = (unsigned)i;
+    if (rem < 5)  // five threads share the owner table of this triangle's rows
+        for (int r = rem; r < s.rows; r += 5) rowOwner[s.rowBase + r] = (unsigned)i;
     const int j = (e + 1) % 3;  // :707
     const int n = abs(s.vy[e] - s.vy[j]) + 1;  // :712
     unsigned off = s.sampleBase;
     for (int k = 0; k < e; ++k) off += (unsigned)(abs(s.vy[k] - s.vy[(k + 1) % 3]) + 1);
     const float div = (float)max(n - 1, 1);  // :622
-    // Pixel operator- (TestModel.h:82-85) then fPixel operator/ (:124-127)
-    const float sx = xdiv_step((float)(s.vx[j] - s.vx[e]), div);
-    const float sz = xdiv_step(xsub(s.vz[j], s.vz[e]), div);
-    const V3 a3 = mk3(s.vp[3 * e], s.vp[3 * e + 1], s.vp[3 * e + 2]);
-    const V3 b3 = mk3(s.vp[3 * j], s.vp[3 * j + 1], s.vp[3 * j + 2]);
-    const V3 d3 = xsub3(b3, a3);
-    const V3 sp = mk3(xdiv_step(d3.x, div), xdiv_step(d3.y, div), xdiv_step(d3.z, div));
-    float cx = (float)s.vx[e], cz = s.vz[e];  // fPixel(Pixel&)
-    V3 cp = a3;
-    EdgeSample* out = samples + off;
-    for (int k = 0; k < n; ++k) {  // :626-636 -- serial float accumulation, order matters
-        EdgeSample q;
-        q.x = f2i_x86(cx);
-        q.zinv = cz;
-        q.p[0] = cp.x;
-        q.p[1] = cp.y;
-        q.p[2] = cp.z;
-        out[k] = q;
-        cx = xadd(cx, sx);
-        cz = xadd(cz, sz);
-        cp = xadd3(cp, sp);
+    // Pixel operator- (TestModel.h:82-85) then fPixel operator/ (:124-127); fPixel(Pixel&) for the start value
+    float cur, step;
+    if (ch == 0) {
+        cur = (float)s.vx[e];
+        step = xdiv_step((float)(s.vx[j] - s.vx[e]), div);
+    } else if (ch == 1) {
+        cur = s.vz[e];
+        step = xdiv_step(xsub(s.vz[j], s.vz[e]), div);
+    } else {
+        cur = s.vp[3 * e + (ch - 2)];
+        step = xdiv_step(xsub(s.vp[3 * j + (ch - 2)], cur), div);
+    }
+    float* out = reinterpret_cast<float*>(samples + off) + ch;  // field ch of sample 0; samples are 5 words apart
+    if (ch == 0) {
+        for (int k = 0; k < n; ++k, out += 5) {  // :626-636 -- serial float accumulation, order matters
+            *reinterpret_cast<int*>(out) = f2i_x86(cur);
+            cur = xadd(cur, step);
+        }
+    } else {
+        for (int k = 0; k < n; ++k, out += 5) {
+            *out = cur;
+            cur = xadd(cur, step);
+        }
     }
 }
 
@@ -692,7 +697,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
         scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, nBig);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
         scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
-        ras_edges_kernel<<<(3 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, samples, owner);
+        ras_edges_kernel<<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, samples, owner);
         ras_rows_kernel<<<(nRows + 255) / 256, 256, 0, s>>>(ts, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
         c->launches += 5;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -20,6 +20,16 @@ if which == "rt":
         ctx.rt_draw_device_async(0, H, col.data_ptr())
         ctx.resolve_surface_device_async(0, H, col.data_ptr(), 0, surf.data_ptr())
     ctx.synchronize()
+elif which == "ras30":
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    ctx.set_frame(pkg.default_frame_params(1, W, H))
+    ctx.ras_cull()
+    dep = torch.empty((H, W), dtype=torch.float32, device=dev)
+    col = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    for _ in range(3):
+        ctx.ras_draw_device_async(0, H, dep.data_ptr(), col.data_ptr())
+    ctx.synchronize()
 else:
     big = pkg.tessellate(tris, 183)
     ctx = pkg.Context(W, H)
