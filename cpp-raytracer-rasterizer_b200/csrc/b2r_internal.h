@@ -61,6 +61,7 @@ struct RtLaunch {
     float* focal;                       // may be null
     unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
     int useFilter;
+    int shadowCache;   // set by launch_rt_trace_shade: per-warp shadow-candidate cache in shared memory
 };
 
 // Frame constants the rasteriser kernels need, passed by value in the kernel-parameter bank.

@@ -398,6 +398,10 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     for (int i = threadIdx.x; i < f->nLights; i += kThreads)
         sPow[i] = make_float4(f->lightPower[i][0], f->lightPower[i][1], f->lightPower[i][2], 0.f);
     uint2* sTileList = reinterpret_cast<uint2*>(sPow + f->nLights);  // 8 warps * nChunks entries (chunk, mask)
+    // Shadow-candidate cache, per warp and light sample: 2 quads (box lo, box hi + mask/count) followed, for
+    // scenes of more than one 32-triangle chunk, by the (chunk, mask) list.  See "cached shadow candidates" below.
+    const int cacheQuads = a.shadowCache ? 2 + (nChunks > 1 ? (nChunks + 1) / 2 : 0) : 0;
+    float4* sShadowCache = reinterpret_cast<float4*>(sTileList + (size_t)(kThreads / 32) * (((nChunks + 1) >> 1) << 1));
     __syncthreads();
 
     const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* myTileList = sTileList + warp * nChunks;  // non-empty chunks of this warp's tile
+    float4* myCache = sShadowCache + (size_t)warp * (nO - 1) * cacheQuads;
     int nList = 0;
     Counters cnt;
     unsigned tile0 = 0u;  // tile mask of the only chunk when T <= 32
@@ -445,6 +450,19 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
             }
             if (nChunks > 1) __syncwarp();
         }
+        // No candidate triangle for any sub-sample of any pixel of the tile: every ClosestIntersection call returns
+        // false, nothing is shaded and the pixel keeps Update()'s reset values; skip the N*N loop.
+        const bool tileEmpty = (nChunks == 1) ? tile0 == 0u : nList == 0;
+        if constexpr (STATS) {
+            if (tileEmpty && inside) cnt.primary += (unsigned long long)(N * N);  // rays the reference casts
+        }
+        if (cacheQuads && !tileEmpty) {  // new tile: empty boxes contain nothing, so the first sample rebuilds
+            for (int o = lane; o < nO - 1; o += 32) {
+                myCache[(size_t)o * cacheQuads] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
+                myCache[(size_t)o * cacheQuads + 1] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+            }
+            __syncwarp();
+        }
 
         PixelState ps;  // Update()'s per-frame reset, raytracer.cpp:335-339 (+P5)
         ps.pos = mk3(0.f, 0.f, 0.f);
@@ -453,20 +471,23 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
         ps.focal = 0.f;
         V3 avg = mk3(0.f, 0.f, 0.f);
         float y1 = (N > 1) ? xsub((float)y, 0.5f) : (float)y;  // :564-567
-        for (int z = 0; z < N; ++z) {
+        for (int z = 0; z < (tileEmpty ? 0 : N); ++z) {
             float x1 = (N > 1) ? xsub((float)x, 0.5f) : (float)x;  // :571-574
             for (int z2 = 0; z2 < N; ++z2) {
                 // ---- primary ray :579-580
                 const float dx = xsub(x1, halfW), dy = xsub(y1, halfH);
-                const V3 dir = xmat_vec(R, mk3(dx, dy, focalLength));
-                const V3 nd = neg3(dir);  // :229
-                bool any = false;
+                V3 nd = mk3(0.f, 0.f, 0.f);
+                bool haveDir = false, any = false;
                 if (inside) {
                     if constexpr (STATS) cnt.primary++;
                     for (int e = 0; e < nList; ++e) {
                         const uint2 cm = (nChunks > 1) ? myTileList[e] : make_uint2(0u, tile0);
                         const int base = (int)cm.x * 32;
                         unsigned m = primary_ray_mask<FILTER>(sF, base, cm.y, dx, dy);
+                        if (m && !haveDir) {  // the direction is only needed by the exact test
+                            nd = neg3(xmat_vec(R, mk3(dx, dy, focalLength)));  // :580, :229
+                            haveDir = true;
+                        }
                         for (; m; m &= m - 1) {  // ascending triangle index
                             const int i = base + __ffs(m) - 1;
                             if constexpr (STATS) cnt.exact++;
@@ -519,31 +540,91 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                             bool occluded = false;
                             const float4* xs = sX + (size_t)2 * o * T;
                             const float4* Fo = sF + (size_t)3 * o * T;
-                            V3 qlo = mk3(0.f, 0.f, 0.f), qhi = mk3(0.f, 0.f, 0.f);
-                            float rb = 0.f;
-                            if (TILECULL && FILTER) {
-                                const float big = 3.0e38f;
-                                qlo = mk3(warp_min(any ? dv.x : big), warp_min(any ? dv.y : big), warp_min(any ? dv.z : big));
-                                qhi = mk3(warp_max(any ? dv.x : -big), warp_max(any ? dv.y : -big), warp_max(any ? dv.z : -big));
-                                const float mx = fmaxf(fabsf(qlo.x), fabsf(qhi.x)), my = fmaxf(fabsf(qlo.y), fabsf(qhi.y)),
-                                            mz = fmaxf(fabsf(qlo.z), fabsf(qhi.z));
-                                rb = sqrtf(fmaf(mx, mx, fmaf(my, my, mz * mz))) * 1.00001f;
-                            }
-                            for (int c = 0; c < nChunks; ++c) {
-                                const int base = c * 32;
-                                unsigned wm;
-                                if (TILECULL) wm = shadow_warp_mask<FILTER>(Fo, base, T, lane, qlo, qhi, rb);
-                                else wm = (T - base >= 32) ? kFull : ((1u << (T - base)) - 1u);
-                                if (any && !occluded) {
-                                    unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir, thr);
-                                    for (; m; m &= m - 1) {
-                                        const int i = base + __ffs(m) - 1;
-                                        if constexpr (STATS) cnt.exact++;
-                                        V3 pos;
-                                        float dist;
-                                        if (exact_hit(sG + i * kGeomQuads, xs + 2 * i, lpos, rDir, pos, dist) && dist < thr) {
-                                            occluded = true;
-                                            break;
+                            // One candidate chunk: per-ray filter, then the exact test in ascending index.
+                            auto shadow_chunk = [&](int base, unsigned wm) {
+                                unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir, thr);
+                                for (; m; m &= m - 1) {
+                                    const int i = base + __ffs(m) - 1;
+                                    if constexpr (STATS) cnt.exact++;
+                                    V3 pos;
+                                    float dist;
+                                    if (exact_hit(sG + i * kGeomQuads, xs + 2 * i, lpos, rDir, pos, dist) && dist < thr) {
+                                        occluded = true;
+                                        break;
+                                    }
+                                }
+                            };
+                            if (!(TILECULL && FILTER)) {
+                                for (int c = 0; c < nChunks; ++c) {
+                                    const int base = c * 32;
+                                    const unsigned wm = (T - base >= 32) ? kFull : ((1u << (T - base)) - 1u);
+                                    if (any && !occluded) shadow_chunk(base, wm);
+                                }
+                            } else {
+                                // Cached shadow candidates.  The warp mask of shadow_warp_mask() is valid for ANY
+                                // box that contains the light->hit vectors of the warp's lit lanes.  The N*N
+                                // sub-samples of a tile hit almost the same surface points, so the box of one
+                                // sample, padded, usually contains those of the following samples: the masks are
+                                // kept (per warp and light sample) together with their box and reused while every
+                                // lane's vector stays inside -- 6 compares and a vote instead of 6 warp reductions
+                                // and the 3-form bound.  A miss rebuilds from the union of the old and the new box.
+                                float4* hdr = myCache + (size_t)(o - 1) * cacheQuads;
+                                uint2* shList = reinterpret_cast<uint2*>(hdr + 2);
+                                unsigned wm0 = 0u;
+                                int nSh = 0;
+                                bool cached = false;
+                                if (cacheQuads) {
+                                    const float4 c0 = hdr[0], c1 = hdr[1];
+                                    const bool in = !any || (dv.x >= c0.x && dv.x <= c1.x && dv.y >= c0.y && dv.y <= c1.y &&
+                                                             dv.z >= c0.z && dv.z <= c1.z);
+                                    cached = __all_sync(kFull, in);
+                                    if (cached) {
+                                        wm0 = __float_as_uint(c1.w);
+                                        nSh = (int)wm0;
+                                    }
+                                }
+                                if (!cached) {
+                                    const float big = 3.0e38f;
+                                    V3 qlo = mk3(warp_min(any ? dv.x : big), warp_min(any ? dv.y : big), warp_min(any ? dv.z : big));
+                                    V3 qhi = mk3(warp_max(any ? dv.x : -big), warp_max(any ? dv.y : -big), warp_max(any ? dv.z : -big));
+                                    if (cacheQuads) {
+                                        const float4 c0 = hdr[0], c1 = hdr[1];
+                                        const float px = fmaf(0.25f, qhi.x - qlo.x, 9.765625e-4f * fmaxf(fabsf(qlo.x), fabsf(qhi.x)));
+                                        const float py = fmaf(0.25f, qhi.y - qlo.y, 9.765625e-4f * fmaxf(fabsf(qlo.y), fabsf(qhi.y)));
+                                        const float pz = fmaf(0.25f, qhi.z - qlo.z, 9.765625e-4f * fmaxf(fabsf(qlo.z), fabsf(qhi.z)));
+                                        qlo = mk3(fminf(c0.x, qlo.x - px), fminf(c0.y, qlo.y - py), fminf(c0.z, qlo.z - pz));
+                                        qhi = mk3(fmaxf(c1.x, qhi.x + px), fmaxf(c1.y, qhi.y + py), fmaxf(c1.z, qhi.z + pz));
+                                    }
+                                    const float mx = fmaxf(fabsf(qlo.x), fabsf(qhi.x)), my = fmaxf(fabsf(qlo.y), fabsf(qhi.y)),
+                                                mz = fmaxf(fabsf(qlo.z), fabsf(qhi.z));
+                                    const float rb = sqrtf(fmaf(mx, mx, fmaf(my, my, mz * mz))) * 1.00001f;
+                                    if (cacheQuads) __syncwarp();  // every lane has read the old list
+                                    for (int c = 0; c < nChunks; ++c) {
+                                        const unsigned wm = shadow_warp_mask<FILTER>(Fo, c * 32, T, lane, qlo, qhi, rb);
+                                        if (nChunks == 1) {
+                                            wm0 = wm;
+                                        } else if (!cacheQuads) {
+                                            if (any && !occluded) shadow_chunk(c * 32, wm);
+                                        } else if (wm) {
+                                            if (lane == 0) shList[nSh] = make_uint2((unsigned)c, wm);
+                                            ++nSh;
+                                        }
+                                    }
+                                    if (cacheQuads) {
+                                        if (lane == 0) {
+                                            hdr[0] = make_float4(qlo.x, qlo.y, qlo.z, 0.f);
+                                            hdr[1] = make_float4(qhi.x, qhi.y, qhi.z, __uint_as_float(nChunks == 1 ? wm0 : (unsigned)nSh));
+                                        }
+                                        __syncwarp();
+                                    }
+                                }
+                                if (any) {
+                                    if (nChunks == 1) {
+                                        shadow_chunk(0, wm0);
+                                    } else if (cacheQuads) {
+                                        for (int e = 0; e < nSh && !occluded; ++e) {
+                                            const uint2 cm = shList[e];
+                                            shadow_chunk((int)cm.x * 32, cm.y);
                                         }
                                     }
                                 }
@@ -594,9 +675,18 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     }
 }
 
-static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident) {
+// Bytes of the per-warp shadow-candidate cache (0 = not used: too many light samples for the space it would take).
+static size_t rt_cache_bytes(int T, int nO) {
+    const size_t nChunks = (size_t)(T + 31) / 32;
+    const size_t quads = 2 + (nChunks > 1 ? (nChunks + 1) / 2 : 0);
+    const size_t bytes = (size_t)(kThreads / 32) * (size_t)(nO > 1 ? nO - 1 : 0) * quads * 16;
+    return bytes <= 32 * 1024 ? bytes : 0;
+}
+
+static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident, bool cache) {
     const size_t quads = (resident ? (size_t)T * kGeomQuads + (size_t)nO * T * 5 : 0) + nO + nLights;
-    return quads * 16 + (size_t)(kThreads / 32) * ((T + 31) / 32) * 8 + 16;
+    const size_t nChunks = (size_t)(T + 31) / 32;
+    return quads * 16 + (size_t)(kThreads / 32) * ((nChunks + 1) / 2 * 2) * 8 + (cache ? rt_cache_bytes(T, nO) : 0) + 16;
 }
 
 template <bool RESIDENT, bool TILECULL>
@@ -618,17 +708,20 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
 }
 
 // B2R_OPT_RT_VARIANT: 0 = tile/warp culling + per-ray filter (default); 1 = per-ray filter only;
-// 2 = like 0 but constants read from HBM even when they would fit in shared memory (tests the large-scene path).
+// 2 = like 0 but constants read from HBM even when they would fit in shared memory (tests the large-scene path);
+// 3 = like 0 without the shadow-candidate cache.
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const DevFrame& f = c->hostFrame;
     RtLaunch a = a0;
-    const size_t smemRes = rt_smem_bytes(a.T, f.nOrigins, f.nLights, true);
+    const bool cache = rt_cache_bytes(a.T, f.nOrigins) > 0 && c->optRtVariant != 3;
+    a.shadowCache = cache ? 1 : 0;
+    const size_t smemRes = rt_smem_bytes(a.T, f.nOrigins, f.nLights, true, cache);
     const bool resident = smemRes <= 96 * 1024 && c->optRtVariant != 2;
     if (resident) {
         a.xconst = a.fconst = nullptr;
         return c->optRtVariant == 1 ? launch_variant<true, false>(c, a, smemRes, s) : launch_variant<true, true>(c, a, smemRes, s);
     }
-    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false);
+    const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false, cache);
     if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > ~100k triangles: reported as B2R_E_UNSUPPORTED
     const size_t pairs = (size_t)f.nOrigins * (size_t)a.T;
     cudaError_t e;

@@ -20,12 +20,13 @@ def rt4k(pkg):
 
 
 def test_rt_culling_levels_agree_on_config3(pkg, rt4k):
-    """Config 3 (AA 4x4) on 216 rows spread over the frame: every culling level off == all on, bit for bit."""
+    """Config 3 (AA 4x4) on 216 rows spread over the frame: every culling level off == all on
+    == all on without the shadow-candidate cache (variant 3), bit for bit."""
     fp = pkg.default_frame_params(0, W, H)
     fp.aaEnabled, fp.aaSamples = 1, 4
     rt4k.set_frame(fp)
     outs = []
-    for filt, variant in ((1, 0), (1, 1), (0, 0)):
+    for filt, variant in ((1, 0), (1, 1), (1, 3), (0, 0)):
         rt4k.set_option(pkg.capi.OPT_RT_FILTER, filt)
         rt4k.set_option(pkg.capi.OPT_RT_VARIANT, variant)
         parts = [rt4k.rt_draw(y0, y0 + 24) for y0 in range(0, H, 240)]
