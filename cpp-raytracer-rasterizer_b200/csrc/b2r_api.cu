@@ -356,6 +356,18 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.geom = c->geom.as<float4>();
     a.xconst = a.fconst = nullptr;
     a.frame = c->frame.as<DevFrame>();
+    {
+        const DevFrame& hf = c->hostFrame;
+        RtFrame& r = a.fr;
+        for (int i = 0; i < 3; ++i) r.cam[i] = hf.cam[i], r.indirect[i] = hf.indirect[i];
+        for (int i = 0; i < 9; ++i) r.R[i] = hf.R[i];
+        r.focal = hf.focal;
+        r.dofFocal = hf.dofFocal;
+        r.aaN = hf.aaN;
+        r.nLights = hf.nLights;
+        r.samples = hf.samples;
+        r.nOrigins = hf.nOrigins;
+    }
     a.T = c->T;
     a.W = c->W;
     a.H = c->H;

@@ -48,7 +48,17 @@ constexpr int kGeomQuads = 5;
 // Per (ray origin, triangle): 2 float4 of exact constants  (be2.xyz, e1e2b), (e1b.xyz, 0)
 // (raytracer.cpp:218,226-227,231) and 3 float4 of conservative filter forms (see rt_trace.cu).
 
+// Frame constants the raytracer's per-sample code needs, passed by value in the kernel-parameter bank so they live
+// in uniform registers instead of per-thread registers (the light-sample origins stay in DevFrame).
+struct RtFrame {
+    float cam[3], focal;
+    float R[9], dofFocal;
+    float indirect[3];
+    int aaN, nLights, samples, nOrigins;
+};
+
 struct RtLaunch {
+    RtFrame fr;
     const float4* geom;      // T * kGeomQuads
     const float4* xconst;    // large scenes only: nO * T * 2 exact (origin,triangle) constants in HBM
     const float4* fconst;    // large scenes only: nO * T * 3 filter forms in HBM

@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
     const DevFrame* __restrict__ f = a.frame;
-    const int nO = f->nOrigins;
+    const int nO = a.fr.nOrigins;
     const int nChunks = (T + 31) >> 5;
     const float4 *sG, *sX, *sF;  // triangle records, exact (origin,triangle) constants, filter forms
     float4* sOrg;                // nO ray origins, then nLights light powers, then the per-warp tile lists
@@ -395,22 +395,20 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
             sOrg[i] = make_float4(f->origin[i][0], f->origin[i][1], f->origin[i][2], 0.f);
     }
     float4* sPow = sOrg + nO;
-    for (int i = threadIdx.x; i < f->nLights; i += kThreads)
+    for (int i = threadIdx.x; i < a.fr.nLights; i += kThreads)
         sPow[i] = make_float4(f->lightPower[i][0], f->lightPower[i][1], f->lightPower[i][2], 0.f);
-    uint2* sTileList = reinterpret_cast<uint2*>(sPow + f->nLights);  // 8 warps * nChunks entries (chunk, mask)
+    uint2* sTileList = reinterpret_cast<uint2*>(sPow + a.fr.nLights);  // 8 warps * nChunks entries (chunk, mask)
     // Shadow-candidate cache, per warp and light sample: 2 quads (box lo, box hi + mask/count) followed, for
     // scenes of more than one 32-triangle chunk, by the (chunk, mask) list.  See "cached shadow candidates" below.
     const int cacheQuads = a.shadowCache ? 2 + (nChunks > 1 ? (nChunks + 1) / 2 : 0) : 0;
     float4* sShadowCache = reinterpret_cast<float4*>(sTileList + (size_t)(kThreads / 32) * (((nChunks + 1) >> 1) << 1));
     __syncthreads();
 
-    const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
-    float R[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = f->R[i];
-    const float focalLength = f->focal, dofFocal = f->dofFocal;
-    const V3 indirect = mk3(f->indirect[0], f->indirect[1], f->indirect[2]);
-    const int N = f->aaN, nLights = f->nLights, samples = f->samples;
+    const V3 cam = mk3(a.fr.cam[0], a.fr.cam[1], a.fr.cam[2]);
+    const float* R = a.fr.R;
+    const float focalLength = a.fr.focal, dofFocal = a.fr.dofFocal;
+    const V3 indirect = mk3(a.fr.indirect[0], a.fr.indirect[1], a.fr.indirect[2]);
+    const int N = a.fr.aaN, nLights = a.fr.nLights, samples = a.fr.samples;
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
     const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
     const float invNN = (float)(N * N);
@@ -515,11 +513,19 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                         colr = mk3(g3.w, g4.x, g4.y);
                     }
                     V3 result = mk3(0.f, 0.f, 0.f), result2 = mk3(0.f, 0.f, 0.f);
-                    for (int k = 0; k < nLights; ++k) {
-                        const float4 pw = sPow[k];
-                        const V3 P = mk3(pw.x, pw.y, pw.z);  // (color*intensity)/samples :282,296
-                        for (int s = 0; s < samples; ++s) {
-                            const int o = 1 + k * samples + s;
+                    // The loops over lights (:279) and their samples (:283) run as one loop over the shadow-ray
+                    // origins o = 1 + k*samples + s with running pointers into the per-origin tables.
+                    const float4* xs = sX + (size_t)2 * T;  // exact constants of origin 1
+                    const float4* Fo = sF + (size_t)3 * T;  // filter forms of origin 1
+                    float4* hdr = myCache;
+                    int kLight = 0, sLeft = samples;
+                    V3 P = mk3(0.f, 0.f, 0.f);  // (color*intensity)/samples :282,296
+                    if (nLights > 0) {
+                        const float4 pw = sPow[0];
+                        P = mk3(pw.x, pw.y, pw.z);
+                    }
+                    for (int o = 1; o < nO; ++o, xs += 2 * T, Fo += 3 * T, hdr += cacheQuads) {
+                        {
                             const float4 og = sOrg[o];
                             const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
                             const V3 dv = xsub3(lpos, ps.pos);       // position - i.position
@@ -538,8 +544,6 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                             // closer than r*0.99f (== j.distance < r*0.99f, j the closest hit)
                             const float thr = xmul(r, 0.99f);
                             bool occluded = false;
-                            const float4* xs = sX + (size_t)2 * o * T;
-                            const float4* Fo = sF + (size_t)3 * o * T;
                             // One candidate chunk: per-ray filter, then the exact test in ascending index.
                             auto shadow_chunk = [&](int base, unsigned wm) {
                                 unsigned m = shadow_ray_mask<FILTER>(Fo, base, wm, rDir, thr);
@@ -568,7 +572,6 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                                 // kept (per warp and light sample) together with their box and reused while every
                                 // lane's vector stays inside -- 6 compares and a vote instead of 6 warp reductions
                                 // and the 3-form bound.  A miss rebuilds from the union of the old and the new box.
-                                float4* hdr = myCache + (size_t)(o - 1) * cacheQuads;
                                 uint2* shList = reinterpret_cast<uint2*>(hdr + 2);
                                 unsigned wm0 = 0u;
                                 int nSh = 0;
@@ -632,7 +635,14 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                             if (occluded) D = mk3(0.f, 0.f, 0.f);
                             result = xadd3(result, D);      // :319
                         }
-                        result2 = xadd3(result2, result);   // :322 (result is not reset per light)
+                        if (--sLeft == 0) {                     // last sample of this light
+                            result2 = xadd3(result2, result);   // :322 (result is not reset per light)
+                            sLeft = samples;
+                            if (++kLight < nLights) {
+                                const float4 pw = sPow[kLight];
+                                P = mk3(pw.x, pw.y, pw.z);
+                            }
+                        }
                     }
                     if (any) {
                         const V3 color = xmul3(result2, colr);  // :325-326
