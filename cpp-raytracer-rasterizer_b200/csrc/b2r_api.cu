@@ -363,6 +363,10 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
         for (int i = 0; i < 9; ++i) r.R[i] = hf.R[i];
         r.focal = hf.focal;
         r.dofFocal = hf.dofFocal;
+        for (int i = 0; i < 3; ++i) {
+            volatile float prod = hf.R[6 + i] * hf.focal;  // one IEEE single multiplication, as the reference's m[2][i]*v.z
+            r.Rf[i] = prod;
+        }
         r.aaN = hf.aaN;
         r.nLights = hf.nLights;
         r.samples = hf.samples;

@@ -53,6 +53,7 @@ constexpr int kGeomQuads = 5;
 struct RtFrame {
     float cam[3], focal;
     float R[9], dofFocal;
+    float Rf[3];       // cameraRot column 2 * focalLength, the third product of cameraRot * vec3(dx, dy, focalLength)
     float indirect[3];
     int aaN, nLights, samples, nOrigins;
 };

@@ -348,21 +348,28 @@ __global__ void __launch_bounds__(256) rt_origin_setup_kernel(const float4* __re
 // The kernel.  RESIDENT: triangles and constants live in shared memory (staged/computed per CTA); otherwise they
 // are read from HBM.  TILECULL = false keeps only the per-ray filter (every ray looks at every triangle).
 // ---------------------------------------------------------------------------
-template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS>
+// SINGLE (implies RESIDENT): at most 32 triangles, i.e. one chunk.  The tables then sit at compile-time offsets
+// (32 triangle slots; per origin one block of 32*2 exact quads followed by 32*3 form quads), so the per-sample code
+// carries no address arithmetic and no chunk loops.
+constexpr int kSingleBlockQuads = 32 * 5;
+template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS, bool SINGLE>
 __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
+    static_assert(RESIDENT || !SINGLE, "SINGLE needs the shared-memory tables");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
     const DevFrame* __restrict__ f = a.frame;
     const int nO = a.fr.nOrigins;
-    const int nChunks = (T + 31) >> 5;
+    const int nChunks = SINGLE ? 1 : (T + 31) >> 5;
+    // quads from one origin's table to the next: exact constants / filter forms
+    const int oStrideX = SINGLE ? kSingleBlockQuads : 2 * T, oStrideF = SINGLE ? kSingleBlockQuads : 3 * T;
     const float4 *sG, *sX, *sF;  // triangle records, exact (origin,triangle) constants, filter forms
     float4* sOrg;                // nO ray origins, then nLights light powers, then the per-warp tile lists
     if constexpr (RESIDENT) {
-        float4* g = reinterpret_cast<float4*>(smem_raw);   // T * kGeomQuads
-        float4* x = g + (size_t)T * kGeomQuads;            // nO * T * 2
-        float4* ff = x + (size_t)nO * T * 2;               // nO * T * 3
-        sOrg = ff + (size_t)nO * T * 3;
+        float4* g = reinterpret_cast<float4*>(smem_raw);                       // T * kGeomQuads
+        float4* x = g + (SINGLE ? 32 * kGeomQuads : (size_t)T * kGeomQuads);   // nO * T * 2
+        float4* ff = SINGLE ? x + 32 * 2 : x + (size_t)nO * T * 2;             // nO * T * 3
+        sOrg = SINGLE ? x + (size_t)nO * kSingleBlockQuads : ff + (size_t)nO * T * 3;
         // 1. triangles: HBM -> shared memory by one bulk async copy (TMA), completion on an mbarrier
         const uint32_t geomBytes = (uint32_t)T * kGeomQuads * 16u;
         if (threadIdx.x == 0) {
@@ -381,7 +388,8 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
         // 2. per (origin, triangle) constants, once per CTA
         for (int it = threadIdx.x; it < nO * T; it += kThreads) {
             const int o = it / T, i = it - o * T;
-            write_pair_constants(g + (size_t)i * kGeomQuads, sOrg[o], o == 0, f, FILTER, x + 2 * it, ff + 3 * it);
+            write_pair_constants(g + (size_t)i * kGeomQuads, sOrg[o], o == 0, f, FILTER, x + (size_t)o * oStrideX + 2 * i,
+                                 ff + (size_t)o * oStrideF + 3 * i);
         }
         sG = g;
         sX = x;
@@ -406,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
 
     const V3 cam = mk3(a.fr.cam[0], a.fr.cam[1], a.fr.cam[2]);
     const float* R = a.fr.R;
-    const float focalLength = a.fr.focal, dofFocal = a.fr.dofFocal;
+    const float dofFocal = a.fr.dofFocal;
     const V3 indirect = mk3(a.fr.indirect[0], a.fr.indirect[1], a.fr.indirect[2]);
     const int N = a.fr.aaN, nLights = a.fr.nLights, samples = a.fr.samples;
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
@@ -483,7 +491,11 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                         const int base = (int)cm.x * 32;
                         unsigned m = primary_ray_mask<FILTER>(sF, base, cm.y, dx, dy);
                         if (m && !haveDir) {  // the direction is only needed by the exact test
-                            nd = neg3(xmat_vec(R, mk3(dx, dy, focalLength)));  // :580, :229
+                            // cameraRot * vec3(dx, dy, focalLength), the third products (column 2 * focalLength)
+                            // taken from the frame constants                                        :580, :229
+                            nd = neg3(mk3(xadd(xadd(xmul(R[0], dx), xmul(R[3], dy)), a.fr.Rf[0]),
+                                          xadd(xadd(xmul(R[1], dx), xmul(R[4], dy)), a.fr.Rf[1]),
+                                          xadd(xadd(xmul(R[2], dx), xmul(R[5], dy)), a.fr.Rf[2])));
                             haveDir = true;
                         }
                         for (; m; m &= m - 1) {  // ascending triangle index
@@ -515,8 +527,8 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                     V3 result = mk3(0.f, 0.f, 0.f), result2 = mk3(0.f, 0.f, 0.f);
                     // The loops over lights (:279) and their samples (:283) run as one loop over the shadow-ray
                     // origins o = 1 + k*samples + s with running pointers into the per-origin tables.
-                    const float4* xs = sX + (size_t)2 * T;  // exact constants of origin 1
-                    const float4* Fo = sF + (size_t)3 * T;  // filter forms of origin 1
+                    const float4* xs = sX + oStrideX;  // exact constants of origin 1
+                    const float4* Fo = sF + oStrideF;  // filter forms of origin 1
                     float4* hdr = myCache;
                     int kLight = 0, sLeft = samples;
                     V3 P = mk3(0.f, 0.f, 0.f);  // (color*intensity)/samples :282,296
@@ -524,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                         const float4 pw = sPow[0];
                         P = mk3(pw.x, pw.y, pw.z);
                     }
-                    for (int o = 1; o < nO; ++o, xs += 2 * T, Fo += 3 * T, hdr += cacheQuads) {
+                    for (int o = 1; o < nO; ++o, xs += oStrideX, Fo += oStrideF, hdr += cacheQuads) {
                         {
                             const float4 og = sOrg[o];
                             const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
@@ -694,15 +706,18 @@ static size_t rt_cache_bytes(int T, int nO) {
 }
 
 static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident, bool cache) {
-    const size_t quads = (resident ? (size_t)T * kGeomQuads + (size_t)nO * T * 5 : 0) + nO + nLights;
+    const size_t slots = T <= 32 ? 32 : (size_t)T;  // the single-chunk layout has 32 fixed slots
+    const size_t quads = (resident ? slots * kGeomQuads + (size_t)nO * slots * 5 : 0) + nO + nLights;
     const size_t nChunks = (size_t)(T + 31) / 32;
     return quads * 16 + (size_t)(kThreads / 32) * ((nChunks + 1) / 2 * 2) * 8 + (cache ? rt_cache_bytes(T, nO) : 0) + 16;
 }
 
-template <bool RESIDENT, bool TILECULL>
+template <bool RESIDENT, bool TILECULL, bool SINGLE = false>
 static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
-    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true> : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false>)
-                            : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true> : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false>);
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true, SINGLE>
+                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false, SINGLE>)
+                            : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true, SINGLE>
+                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false, SINGLE>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSM = 1;
@@ -729,6 +744,9 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const bool resident = smemRes <= 96 * 1024 && c->optRtVariant != 2;
     if (resident) {
         a.xconst = a.fconst = nullptr;
+        if (a.T <= 32)
+            return c->optRtVariant == 1 ? launch_variant<true, false, true>(c, a, smemRes, s)
+                                        : launch_variant<true, true, true>(c, a, smemRes, s);
         return c->optRtVariant == 1 ? launch_variant<true, false>(c, a, smemRes, s) : launch_variant<true, true>(c, a, smemRes, s);
     }
     const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false, cache);

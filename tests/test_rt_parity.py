@@ -200,12 +200,14 @@ def test_errors(pkg):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 2, 3])
-def test_large_scene_path(pkg, oracle, variant):
-    """Scenes that do not fit in shared memory keep their per-frame constants in HBM (variant 2 forces that path
-    for a small scene too); 2,430 tessellated Cornell triangles with AA and two lights."""
+@pytest.mark.parametrize("variant,k", [(0, 9), (2, 2), (3, 9), (0, 2), (3, 2), (1, 2)])
+def test_large_scene_path(pkg, oracle, variant, k):
+    """More than one 32-triangle chunk.  Scenes that do not fit in shared memory (k=9: 2,430 tessellated Cornell
+    triangles) keep their per-frame constants in HBM; variant 2 forces that path for a small scene too; k=2 (120
+    triangles) is the multi-chunk shared-memory layout; variant 3 = without the shadow-candidate cache.  AA and two
+    lights."""
     w, h = 96, 64
-    tris = pkg.tessellate(pkg.cornell_box(), 2 if variant == 2 else 9)
+    tris = pkg.tessellate(pkg.cornell_box(), k)
     fp = pkg.default_frame_params(0, w, h)
     fp.aaEnabled, fp.aaSamples = 1, 2
     fp.set_lights([[0, -0.5, -0.7, 1, 1, 1, 14], [0.4, -0.2, -0.9, 0.3, 0.6, 0.9, 6]])
