@@ -55,6 +55,7 @@ struct RtFrame {
     float R[9], dofFocal;
     float Rf[3];       // cameraRot column 2 * focalLength, the third product of cameraRot * vec3(dx, dy, focalLength)
     float indirect[3];
+    float light0[3], power0[3];  // single-light variant: origin[1] and lightPower[0]
     int aaN, nLights, samples, nOrigins;
 };
 

@@ -352,14 +352,17 @@ __global__ void __launch_bounds__(256) rt_origin_setup_kernel(const float4* __re
 // (32 triangle slots; per origin one block of 32*2 exact quads followed by 32*3 form quads), so the per-sample code
 // carries no address arithmetic and no chunk loops.
 constexpr int kSingleBlockQuads = 32 * 5;
-template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS, bool SINGLE>
+// ONE (implies SINGLE): one light, one shadow sample (the reference's defaults); the light loop disappears and the
+// light's position and power come from the kernel parameters.
+template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS, bool SINGLE, bool ONE>
 __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
     static_assert(RESIDENT || !SINGLE, "SINGLE needs the shared-memory tables");
+    static_assert(SINGLE || !ONE, "ONE is a specialisation of SINGLE");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const int T = a.T;
     const DevFrame* __restrict__ f = a.frame;
-    const int nO = a.fr.nOrigins;
+    const int nO = ONE ? 2 : a.fr.nOrigins;
     const int nChunks = SINGLE ? 1 : (T + 31) >> 5;
     // quads from one origin's table to the next: exact constants / filter forms
     const int oStrideX = SINGLE ? kSingleBlockQuads : 2 * T, oStrideF = SINGLE ? kSingleBlockQuads : 3 * T;
@@ -416,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
     const float* R = a.fr.R;
     const float dofFocal = a.fr.dofFocal;
     const V3 indirect = mk3(a.fr.indirect[0], a.fr.indirect[1], a.fr.indirect[2]);
-    const int N = a.fr.aaN, nLights = a.fr.nLights, samples = a.fr.samples;
+    const int N = a.fr.aaN, nLights = ONE ? 1 : a.fr.nLights, samples = ONE ? 1 : a.fr.samples;
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
     const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
     const float invNN = (float)(N * N);
@@ -532,13 +535,15 @@ __global__ void __launch_bounds__(kThreads, 3) rt_trace_shade_kernel(const __gri
                     float4* hdr = myCache;
                     int kLight = 0, sLeft = samples;
                     V3 P = mk3(0.f, 0.f, 0.f);  // (color*intensity)/samples :282,296
-                    if (nLights > 0) {
+                    if (ONE) {
+                        P = mk3(a.fr.power0[0], a.fr.power0[1], a.fr.power0[2]);
+                    } else if (nLights > 0) {
                         const float4 pw = sPow[0];
                         P = mk3(pw.x, pw.y, pw.z);
                     }
                     for (int o = 1; o < nO; ++o, xs += oStrideX, Fo += oStrideF, hdr += cacheQuads) {
                         {
-                            const float4 og = sOrg[o];
+                            const float4 og = ONE ? make_float4(a.fr.light0[0], a.fr.light0[1], a.fr.light0[2], 0.f) : sOrg[o];
                             const V3 lpos = mk3(og.x, og.y, og.z);   // :284-291
                             const V3 dv = xsub3(lpos, ps.pos);       // position - i.position
                             const float rr = xdot3(dv, dv);
@@ -712,12 +717,12 @@ static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident, bool cach
     return quads * 16 + (size_t)(kThreads / 32) * ((nChunks + 1) / 2 * 2) * 8 + (cache ? rt_cache_bytes(T, nO) : 0) + 16;
 }
 
-template <bool RESIDENT, bool TILECULL, bool SINGLE = false>
+template <bool RESIDENT, bool TILECULL, bool SINGLE = false, bool ONE = false>
 static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
-    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true, SINGLE>
-                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false, SINGLE>)
-                            : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true, SINGLE>
-                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false, SINGLE>);
+    auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true, SINGLE, ONE>
+                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false, SINGLE, ONE>)
+                            : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true, SINGLE, ONE>
+                                       : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false, SINGLE, ONE>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int perSM = 1;
@@ -744,9 +749,14 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const bool resident = smemRes <= 96 * 1024 && c->optRtVariant != 2;
     if (resident) {
         a.xconst = a.fconst = nullptr;
-        if (a.T <= 32)
+        if (a.T <= 32) {
+            if (f.nLights == 1 && f.samples == 1 && f.nOrigins == 2 && c->optRtVariant == 0) {
+                for (int i = 0; i < 3; ++i) a.fr.light0[i] = f.origin[1][i], a.fr.power0[i] = f.lightPower[0][i];
+                return launch_variant<true, true, true, true>(c, a, smemRes, s);
+            }
             return c->optRtVariant == 1 ? launch_variant<true, false, true>(c, a, smemRes, s)
                                         : launch_variant<true, true, true>(c, a, smemRes, s);
+        }
         return c->optRtVariant == 1 ? launch_variant<true, false>(c, a, smemRes, s) : launch_variant<true, true>(c, a, smemRes, s);
     }
     const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false, cache);
