@@ -155,7 +155,7 @@ int b2r_destroy(b2r_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
-                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->subScratch, &c->stats};
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->rtSched, &c->subScratch, &c->stats};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
@@ -383,6 +383,11 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.closest = d_clo;
     a.focal = d_foc;
     a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
+    if (!c->rtSched.p) {  // the kernel leaves the two words zero again when it finishes
+        CU(c->rtSched.reserve(64), "scheduler alloc");
+        CU(cudaMemsetAsync(c->rtSched.p, 0, 64, c->stream), "scheduler clear");
+    }
+    a.sched = c->rtSched.as<unsigned>();
     a.useFilter = c->optRtFilter;
     cudaError_t e = launch_rt_trace_shade(c, a, c->stream);
     if (e == cudaErrorInvalidConfiguration)

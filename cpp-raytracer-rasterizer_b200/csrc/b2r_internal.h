@@ -72,6 +72,8 @@ struct RtLaunch {
     b2r_intersection* closest;          // may be null
     float* focal;                       // may be null
     unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
+    unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
+    int batch;         // warp tiles per scheduler fetch (set by the launcher)
     int useFilter;
     int shadowCache;   // set by launch_rt_trace_shade: per-warp shadow-candidate cache in shared memory
 };
@@ -173,6 +175,7 @@ struct Ctx {
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
     DevBuf subScratch;  // staging of the sub-stage entry points
+    DevBuf rtSched;   // raytracer: warp-tile scheduler words (RtLaunch::sched)
     DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
     size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
     void* rasKeysCleanPtr = nullptr;

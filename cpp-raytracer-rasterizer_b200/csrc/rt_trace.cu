@@ -431,9 +431,27 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
     Counters cnt;
     unsigned tile0 = 0u;  // tile mask of the only chunk when T <= 32
 
-    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+    // Warp tiles (8x4 pixels; 8 of them form a 32x8 block) are handed out dynamically in batches of a.batch, so
+    // warps that drew empty or cheap tiles keep going instead of idling until the slowest warp is done.  Every
+    // warp's first batch is static (its global index); the following ones come from one atomic each, issued a
+    // batch ahead to hide its latency.
+    const int numWarpTiles = a.numTiles * (kThreads / 32);
+    // a.batch == 0 (small frames): plain static striding, no atomics.
+    const bool dynamic = a.batch > 0;
+    const int batch = dynamic ? a.batch : 1, firstDynamic = (int)gridDim.x * (kThreads / 32) * batch;
+    int base = ((int)blockIdx.x * (kThreads / 32) + warp) * batch;
+    auto fetch_batch = [&]() {
+        if (!dynamic) return base + firstDynamic;
+        int v = 0;
+        if (lane == 0) v = firstDynamic + (int)atomicAdd(a.sched, (unsigned)batch);
+        return __shfl_sync(kFull, v, 0);
+    };
+    int nextBase = base < numWarpTiles ? fetch_batch() : numWarpTiles;
+    for (; base < numWarpTiles; base = nextBase, nextBase = nextBase < numWarpTiles ? fetch_batch() : numWarpTiles)
+    for (int wt = base; wt < min(base + batch, numWarpTiles); ++wt) {
+        const int tile = wt >> 3, sub = wt & 7;
         const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
-        const int wx0 = tx * kTileW + (warp & 3) * 8, wy0 = a.y0 + ty * kTileH + (warp >> 2) * 4;
+        const int wx0 = tx * kTileW + (sub & 3) * 8, wy0 = a.y0 + ty * kTileH + (sub >> 2) * 4;
         const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
         const bool inside = x < a.W && y < a.y1;  // lanes outside stay for the warp collectives
         if (!__any_sync(kFull, inside)) continue;
@@ -691,6 +709,17 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
         }
     }
 
+    // The last CTA of the grid to run out of tiles re-arms the scheduler for the next launch (every other CTA
+    // has made its final fetch before it counts itself as finished).
+    if (dynamic) __syncthreads();
+    if (dynamic && threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.sched + 1, 1u);
+        if (done == gridDim.x - 1u) {
+            a.sched[0] = 0u;
+            a.sched[1] = 0u;
+        }
+    }
+
     if constexpr (STATS) {
         unsigned long long v[3] = {cnt.primary, cnt.shadow, cnt.exact};
 #pragma unroll
@@ -732,7 +761,14 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
     int grid = c->smCount * perSM;
     if (grid > a.numTiles) grid = a.numTiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<grid, kThreads, smem, s>>>(a);
+    // Warp tiles per scheduler fetch, by the work a tile carries (sub-samples x rays per sub-sample); frames with
+    // fewer than 8 tiles per resident warp are strided statically (batch 0).
+    RtLaunch b = a;
+    const int work = a.fr.aaN * a.fr.aaN * a.fr.nOrigins;
+    int batch = work >= 8 ? 1 : (work >= 4 ? 2 : 4);
+    if ((long long)a.numTiles < 8LL * grid) batch = 0;
+    b.batch = batch;
+    kern<<<grid, kThreads, smem, s>>>(b);
     c->launches++;
     return cudaGetLastError();
 }
