@@ -366,6 +366,10 @@ def run_gpu_arm(args, pkg):
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "kernel": "rt_trace_shade_kernel", "kernel_ms": kern_ms,
+                         "exact_tests_frac": st["exact_tests"] / float(rays * len(tris)),
+                         "note": "achieved = SURVEY 8d algorithmic flops (every ray x every triangle) / kernel time; "
+                                 "conservative culling leaves only exact_tests_frac of those tests to execute, so "
+                                 "frac can exceed 1 -- profiles/ has the executed-instruction view (issue slots)",
                          "peak_source": "FFMA microbenchmark measured in this run (b2r_measure_fp32_peak); "
                                         "MEASURED_PEAKS.json has no FP32 entry"},
             "clocks": clocks,

@@ -424,8 +424,16 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
         for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->partDone[i], cudaEventDisableTiming), "cudaEventCreate");
     }
     cudaStream_t drawStream = c->stream;
+    // Only the last sub-band's copy is exposed (the others overlap the next sub-band's tracing), so the sub-bands
+    // shrink towards the end; cuts fall on multiples of the 8-row tile height.
+    static const int kCut4[5] = {0, 32, 60, 84, 100}, kCut2[3] = {0, 64, 100};
+    auto cut = [&](int p) {
+        if (p >= parts) return y1;
+        const int pct = parts == 4 ? kCut4[p] : (parts == 2 ? kCut2[p] : 0);
+        return y0 + (int)((long long)rows * pct / 100) / 8 * 8;
+    };
     for (int p = 0; p < parts; ++p) {
-        const int a0 = y0 + (int)((long long)rows * p / parts), a1 = y0 + (int)((long long)rows * (p + 1) / parts);
+        const int a0 = cut(p), a1 = cut(p + 1);
         if (int rc = rt_launch_band(c, a0, a1, c->colours.as<float>(), clo ? c->closest.as<b2r_intersection>() : nullptr,
                                     needFocal ? c->focal.as<float>() : nullptr))
             return rc;
