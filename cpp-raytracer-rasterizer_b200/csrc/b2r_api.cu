@@ -349,7 +349,8 @@ int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds) {
 }
 
 // ---- raytracer ------------------------------------------------------------------
-static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc) {
+static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
+                          uint32_t* d_surf = nullptr) {
     c->lastDraw = 0;
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
@@ -382,6 +383,7 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.colours = d_col;
     a.closest = d_clo;
     a.focal = d_foc;
+    a.surface = d_surf;
     a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
     if (!c->rtSched.p) {  // the kernel leaves the two words zero again when it finishes
         CU(c->rtSched.reserve(64), "scheduler alloc");
@@ -410,7 +412,10 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
     if (int rc = check_band(c, y0, y1)) return rc;
     if (int rc = reset_stats(c)) return rc;
     const size_t n = (size_t)c->W * c->H;
-    CU(c->colours.reserve(n * 12), "alloc pixelColours");
+    // without depth of field the trace kernel writes the surface itself (and pixelColours only if asked for)
+    const bool fused = surface && !c->params.dofEnabled;
+    const bool needCol = col || (surface && !fused);
+    if (needCol) CU(c->colours.reserve(n * 12), "alloc pixelColours");
     if (clo) CU(c->closest.reserve(n * 20), "alloc closestIntersections");
     const bool needFocal = foc || (surface && c->params.dofEnabled);
     if (needFocal) CU(c->focal.reserve(n * 4), "alloc focalDistances");
@@ -434,10 +439,11 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
     };
     for (int p = 0; p < parts; ++p) {
         const int a0 = cut(p), a1 = cut(p + 1);
-        if (int rc = rt_launch_band(c, a0, a1, c->colours.as<float>(), clo ? c->closest.as<b2r_intersection>() : nullptr,
-                                    needFocal ? c->focal.as<float>() : nullptr))
+        if (int rc = rt_launch_band(c, a0, a1, needCol ? c->colours.as<float>() : nullptr,
+                                    clo ? c->closest.as<b2r_intersection>() : nullptr,
+                                    needFocal ? c->focal.as<float>() : nullptr, fused ? c->surface.as<uint32_t>() : nullptr))
             return rc;
-        if (surface)
+        if (surface && !fused)
             CU(launch_resolve_surface(c, a0, a1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), drawStream),
                "resolve_surface_kernel");
         if (parts > 1) {
@@ -454,6 +460,8 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
     }
     if (parts > 1) CU(cudaStreamSynchronize(c->copyStream), "raytracer draw (copies)");
     CU(cudaStreamSynchronize(c->stream), "raytracer draw");
+    c->coloursValid = needCol;
+    c->surfaceValid = surface && y0 == 0 && y1 == c->H;
     return B2R_OK;
 }
 
@@ -463,6 +471,21 @@ int b2r_rt_draw(b2r_ctx* ctx, int y0, int y1, float* col, b2r_intersection* clo,
     return rt_draw_host(c, y0, y1, col, clo, foc, nullptr);
 }
 
+int b2r_rt_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_col, b2r_intersection* d_clo,
+                              float* d_foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    if (!d_surface) return rt_launch_band(c, y0, y1, d_col, d_clo, d_foc);
+    if (!c->params.dofEnabled) return rt_launch_band(c, y0, y1, d_col, d_clo, d_foc, d_surface);
+    // depth of field: the blur window reads neighbouring rows, so the caller's arrays must hold them already
+    if (!d_col || !d_foc) return fail(c, B2R_E_INVALID, "b2r_rt_frame_device_async: depth of field needs d_pixelColours and d_focalDistances");
+    if (int rc = rt_launch_band(c, y0, y1, d_col, d_clo, d_foc)) return rc;
+    CU(launch_resolve_surface(c, y0, y1, d_col, d_foc, d_surface, c->stream), "resolve_surface_kernel");
+    return B2R_OK;
+}
+
 int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* clo, float* foc) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
@@ -470,11 +493,8 @@ int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* 
 }
 
 // ---- rasteriser -------------------------------------------------------------------
-int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float* d_col, float* d_foc, int32_t* d_win) {
-    Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    if (int rc = bind(c)) return rc;
-    if (int rc = check_band(c, y0, y1)) return rc;
-    if (int rc = reset_stats(c)) return rc;
+static int ras_launch_band(Ctx* c, int y0, int y1, float* d_dep, float* d_col, float* d_foc, int32_t* d_win,
+                           uint32_t* d_surf) {
     c->lastDraw = 1;
     if (y1 == y0) return B2R_OK;
     RasLaunch a;
@@ -514,6 +534,7 @@ int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float*
     a.colours = d_col;
     a.focal = d_foc;
     a.winner = d_win;
+    a.surface = d_surf;
     a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
     cudaError_t e = launch_ras_draw(c, a, c->stream);
     if (e == cudaErrorInvalidValue)
@@ -523,22 +544,48 @@ int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float*
     return B2R_OK;
 }
 
+int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_dep, float* d_col, float* d_foc, int32_t* d_win) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    return ras_launch_band(c, y0, y1, d_dep, d_col, d_foc, d_win, nullptr);
+}
+
+int b2r_ras_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_dep, float* d_col, float* d_foc,
+                               int32_t* d_win) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    if (!d_surface || !c->params.dofEnabled) return ras_launch_band(c, y0, y1, d_dep, d_col, d_foc, d_win, d_surface);
+    if (!d_col || !d_foc) return fail(c, B2R_E_INVALID, "b2r_ras_frame_device_async: depth of field needs d_pixelColours and d_focalDistances");
+    if (int rc = ras_launch_band(c, y0, y1, d_dep, d_col, d_foc, d_win, nullptr)) return rc;
+    CU(launch_resolve_surface(c, y0, y1, d_col, d_foc, d_surface, c->stream), "resolve_surface_kernel");
+    return B2R_OK;
+}
+
 static int ras_draw_host(Ctx* c, int y0, int y1, float* dep, float* col, float* foc, int32_t* win, uint32_t* surface) {
     if (int rc = check_band(c, y0, y1)) return rc;
     const size_t n = (size_t)c->W * c->H;
-    CU(c->colours.reserve(n * 12), "alloc pixelColours");
+    // without depth of field the shade kernel writes the surface itself (and pixelColours only if asked for)
+    const bool fused = surface && !c->params.dofEnabled;
+    const bool needCol = col || (surface && !fused);
+    if (needCol) CU(c->colours.reserve(n * 12), "alloc pixelColours");
     if (dep) CU(c->depth.reserve(n * 4), "alloc depthBuffer");
     if (win) CU(c->winner.reserve(n * 4), "alloc winnerIndex");
+    if (surface) CU(c->surface.reserve(n * 4), "alloc surface");
     const bool needFocal = foc || (surface && c->params.dofEnabled);
     if (needFocal) CU(c->focal.reserve(n * 4), "alloc focalDistances");
-    if (int rc = b2r_ras_draw_device_async(reinterpret_cast<b2r_ctx*>(c), y0, y1, dep ? c->depth.as<float>() : nullptr,
-                                           c->colours.as<float>(), needFocal ? c->focal.as<float>() : nullptr,
-                                           win ? c->winner.as<int32_t>() : nullptr))
+    if (int rc = reset_stats(c)) return rc;
+    if (int rc = ras_launch_band(c, y0, y1, dep ? c->depth.as<float>() : nullptr, needCol ? c->colours.as<float>() : nullptr,
+                                 needFocal ? c->focal.as<float>() : nullptr, win ? c->winner.as<int32_t>() : nullptr,
+                                 fused ? c->surface.as<uint32_t>() : nullptr))
         return rc;
     if (surface) {
-        CU(c->surface.reserve(n * 4), "alloc surface");
-        CU(launch_resolve_surface(c, y0, y1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
-           "resolve_surface_kernel");
+        if (!fused)
+            CU(launch_resolve_surface(c, y0, y1, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+               "resolve_surface_kernel");
         if (int rc = copy_rows_out(c, surface, c->surface.p, y0, y1, 4)) return rc;
     }
     if (int rc = copy_rows_out(c, dep, c->depth.p, y0, y1, 4)) return rc;
@@ -546,6 +593,8 @@ static int ras_draw_host(Ctx* c, int y0, int y1, float* dep, float* col, float* 
     if (int rc = copy_rows_out(c, foc, c->focal.p, y0, y1, 4)) return rc;
     if (int rc = copy_rows_out(c, win, c->winner.p, y0, y1, 4)) return rc;
     CU(cudaStreamSynchronize(c->stream), "rasteriser draw");
+    c->coloursValid = needCol;
+    c->surfaceValid = surface && y0 == 0 && y1 == c->H;
     return B2R_OK;
 }
 
@@ -652,12 +701,14 @@ int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
     if (!surface) return fail(c, B2R_E_INVALID, "null surface");
-    if (c->lastDraw < 0 || !c->colours.p) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    const bool haveSurface = c->surfaceValid && !c->coloursValid;  // fused raytracer frame: already resolved
+    if (c->lastDraw < 0 || (!haveSurface && !c->colours.p)) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
     if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
     const size_t n = (size_t)c->W * c->H;
     CU(c->surface.reserve(n * 4), "alloc surface");
-    CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
-       "resolve_surface_kernel");
+    if (!haveSurface)
+        CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+           "resolve_surface_kernel");
     CU(cudaMemcpyAsync(surface, c->surface.p, n * 4, cudaMemcpyDeviceToHost, c->stream), "surface D2H");
     CU(cudaStreamSynchronize(c->stream), "resolve");
     return B2R_OK;
@@ -672,13 +723,15 @@ int b2r_resolve_bgr8(b2r_ctx* ctx, uint8_t* bgr) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
     if (!bgr) return fail(c, B2R_E_INVALID, "null bgr");
-    if (c->lastDraw < 0 || !c->colours.p) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    const bool haveSurface = c->surfaceValid && !c->coloursValid;  // fused raytracer frame: already resolved
+    if (c->lastDraw < 0 || (!haveSurface && !c->colours.p)) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
     if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
     const size_t n = (size_t)c->W * c->H, payload = b2r_bmp_payload_bytes(c->W, c->H);
     CU(c->surface.reserve(n * 4), "alloc surface");
     CU(c->bgr.reserve(payload), "alloc bgr");
-    CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
-       "resolve_surface_kernel");
+    if (!haveSurface)
+        CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+           "resolve_surface_kernel");
     CU(launch_surface_to_bgr8(c, c->surface.as<uint32_t>(), c->bgr.as<uint8_t>(), c->stream), "surface_to_bgr8_kernel");
     CU(cudaMemcpyAsync(bgr, c->bgr.p, payload, cudaMemcpyDeviceToHost, c->stream), "bgr D2H");
     CU(cudaStreamSynchronize(c->stream), "resolve");

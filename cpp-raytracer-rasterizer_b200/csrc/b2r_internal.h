@@ -71,6 +71,7 @@ struct RtLaunch {
     float* colours;                     // may be null
     b2r_intersection* closest;          // may be null
     float* focal;                       // may be null
+    uint32_t* surface;                  // may be null: the resolved XRGB surface (only without depth of field)
     unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
     unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
     int batch;         // warp tiles per scheduler fetch (set by the launcher)
@@ -102,6 +103,7 @@ struct RasLaunch {
     float* colours;
     float* focal;
     int32_t* winner;
+    uint32_t* surface;         // may be null: the resolved XRGB surface (only without depth of field)
     unsigned long long* stats;
 };
 
@@ -188,6 +190,9 @@ struct Ctx {
     unsigned long long launches = 0;
     int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0;
     int lastDraw = -1;  // 0 raytracer, 1 rasteriser
+    // what the context's own buffers hold after the last host-buffer draw: the fused raytracer frame may leave only
+    // the resolved surface (no pixelColours); b2r_resolve_* then start from it
+    bool coloursValid = false, surfaceValid = false;
 };
 
 }  // namespace b2r

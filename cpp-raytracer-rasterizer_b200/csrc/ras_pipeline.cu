@@ -37,6 +37,7 @@
 
 #include "b2r_internal.h"
 #include "exact.cuh"
+#include "pixel_pack.cuh"
 #include "ras_device.cuh"
 
 namespace b2r {
@@ -563,6 +564,8 @@ __global__ void __launch_bounds__(256, 5) ras_shade_kernel(RasLaunch a, const Tr
         }
         if (a.focal) a.focal[idx] = focal;
         if (a.winner) a.winner[idx] = winner;
+        // CalculateDOF without depth of field + PutPixelSDL (:516-526), fused
+        if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(colour.x, colour.y, colour.z) : 0u;
     }
 }
 

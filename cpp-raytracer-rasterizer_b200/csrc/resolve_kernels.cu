@@ -7,15 +7,9 @@
 // roofline denominator (MEASURED_PEAKS.json has no FP32 entry).
 #include "b2r_internal.h"
 #include "exact.cuh"
+#include "pixel_pack.cuh"
 
 namespace b2r {
-
-__device__ __forceinline__ uint32_t quantise(float c) {
-    float v = xmul(255.0f, c);        // 255*color.r
-    v = (v < 0.f) ? 0.f : v;          // glm::clamp = min(max(x, 0), 255)
-    v = (255.f < v) ? 255.f : v;
-    return __float2uint_rz(v) & 0xFFu;  // Uint8(...)
-}
 
 // Out-of-range policy for the DOF window (the reference reads without bounds checks,
 // raytracer.cpp:637): the flattened index is used as-is inside [0, W*H) (columns wrap into
@@ -34,7 +28,7 @@ __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __res
     const int y = y0 + blockIdx.y;
     if (x >= W) return;
     uint32_t out = 0u;  // the 1-pixel border is never written by the reference: stays black
-    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+    if (inside_border(x, y, W, H)) {
         const long long c = (long long)y * W + x;
         float fr = 0.f, fg = 0.f, fb = 0.f;
         if (dof) {
@@ -59,7 +53,7 @@ __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __res
             fg = colours[3 * c + 1];
             fb = colours[3 * c + 2];
         }
-        out = (quantise(fr) << 16) | (quantise(fg) << 8) | quantise(fb);    // SDL_MapRGB on XRGB8888
+        out = pack_xrgb(fr, fg, fb);
     }
     const size_t o = (size_t)y * W + x;
 #pragma unroll

@@ -39,6 +39,7 @@
 
 #include "b2r_internal.h"
 #include "exact.cuh"
+#include "pixel_pack.cuh"
 #include "rt_device.cuh"
 
 namespace b2r {
@@ -706,6 +707,8 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
                 c->triangleIndex = ps.idx;
             }
             if (a.focal) a.focal[idx] = ps.focal;
+            // CalculateDOF without depth of field + PutPixelSDL (:643-651), fused: no second pass over the colours
+            if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(avg.x, avg.y, avg.z) : 0u;
         }
     }
 

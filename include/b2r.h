@@ -162,6 +162,14 @@ int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_pixelColours
                              b2r_intersection* d_closestIntersections, float* d_focalDistances);
 int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_depthBuffer,
                               float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
+/* Draw() for rows [y0,y1) in one call: trace (or rasterise) + shade + CalculateDOF/PutPixelSDL into d_surface (full-frame
+ * uint32 array).  Without depth of field the surface is written by the trace / shade kernel itself (no second pass;
+ * d_pixelColours / d_focalDistances may be NULL).  With depth of field the rows are resolved by a second kernel
+ * from d_pixelColours / d_focalDistances (required), whose neighbouring rows must already be up to date. */
+int b2r_rt_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_pixelColours,
+                              b2r_intersection* d_closestIntersections, float* d_focalDistances);
+int b2r_ras_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_depthBuffer,
+                               float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
 /* Resolve rows [y0,y1) of d_pixelColours (+ d_focalDistances when DOF is on) into d_surface. */
 int b2r_resolve_surface_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_pixelColours,
                                      const float* d_focalDistances, uint32_t* d_surface);

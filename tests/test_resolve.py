@@ -30,6 +30,9 @@ def test_resolve_surface_and_bmp(pkg, oracle, which, dof, tmp_path):
     assert np.array_equal(bgr, oracle.surface_to_bgr8(want))
     frame = ctx.rt_frame() if which == 0 else ctx.ras_frame()
     assert np.array_equal(frame, want)
+    # without depth of field the frame call is fused (no pixelColours kept): resolving again starts from its surface
+    assert np.array_equal(ctx.resolve_bgr8(), bgr)
+    assert np.array_equal(ctx.resolve_surface(), want)
     path = str(tmp_path / "frame.bmp")
     pkg.write_bmp(path, bgr, w, h)
     raw = open(path, "rb").read()
@@ -48,4 +51,60 @@ def test_bmp_row_padding(pkg, oracle):
     bgr = ctx.resolve_bgr8()
     assert len(bgr) == 100 * h
     assert np.array_equal(bgr, oracle.surface_to_bgr8(oracle.resolve_surface(out["pixelColours"], None)))
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("dof", [0, 1])
+@pytest.mark.parametrize("aa", [0, 1])
+def test_fused_frame_device_equals_draw_then_resolve(pkg, which, dof, aa):
+    """b2r_{rt,ras}_frame_device_async (surface written by the trace / shade kernel itself when depth of field is
+    off) == draw + b2r_resolve_surface_device_async, also band by band and with the optional outputs left out."""
+    import torch
+    w, h = 200, 136
+    dev = torch.device("cuda:0")
+    fp = pkg.default_frame_params(which, w, h)
+    fp.dofEnabled = dof
+    if which == 0:
+        fp.aaEnabled, fp.aaSamples = aa, 3
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(pkg.cornell_box())
+    ctx.set_frame(fp)
+    if which == 1:
+        ctx.ras_cull()
+    col = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    foc = torch.zeros((h, w), dtype=torch.float32, device=dev)
+    ref = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    if which == 0:
+        ctx.rt_draw_device_async(0, h, col.data_ptr(), 0, foc.data_ptr())
+    else:
+        ctx.ras_draw_device_async(0, h, 0, col.data_ptr(), foc.data_ptr(), 0)
+    ctx.resolve_surface_device_async(0, h, col.data_ptr(), foc.data_ptr(), ref.data_ptr())
+    ctx.synchronize()
+    col2, foc2 = torch.zeros_like(col), torch.zeros_like(foc)
+    got = torch.full((h, w), -1, dtype=torch.int32, device=dev)
+    frame = ctx.rt_frame_device_async if which == 0 else ctx.ras_frame_device_async
+    if dof:   # needs the whole frame's colours before any row is resolved: one band
+        bands = [(0, h)]
+    else:
+        bands = [(0, 40), (40, 41), (41, h)]
+    for y0, y1 in bands:
+        if which == 0:
+            frame(y0, y1, got.data_ptr(), col2.data_ptr(), 0, foc2.data_ptr())
+        else:
+            frame(y0, y1, got.data_ptr(), 0, col2.data_ptr(), foc2.data_ptr(), 0)
+    ctx.synchronize()
+    assert torch.equal(got, ref)
+    assert torch.equal(col2.view(torch.int32), col.view(torch.int32))
+    if not dof:  # surface only
+        got2 = torch.full((h, w), -1, dtype=torch.int32, device=dev)
+        if which == 0:
+            frame(0, h, got2.data_ptr())
+        else:
+            frame(0, h, got2.data_ptr())
+        ctx.synchronize()
+        assert torch.equal(got2, ref)
+    else:
+        with pytest.raises(pkg.B2RError):
+            frame(0, h, got.data_ptr())
     ctx.close()
