@@ -349,8 +349,10 @@ int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds) {
 }
 
 // ---- raytracer ------------------------------------------------------------------
+constexpr int kMaxCopyBands = 32;
+
 static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
-                          uint32_t* d_surf = nullptr) {
+                          uint32_t* d_surf = nullptr, int bandTileRows = 0) {
     c->lastDraw = 0;
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
@@ -385,11 +387,13 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.focal = d_foc;
     a.surface = d_surf;
     a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
-    if (!c->rtSched.p) {  // the kernel leaves the two words zero again when it finishes
-        CU(c->rtSched.reserve(64), "scheduler alloc");
-        CU(cudaMemsetAsync(c->rtSched.p, 0, 64, c->stream), "scheduler clear");
+    if (!c->rtSched.p) {  // the kernel leaves the two scheduler words zero again when it finishes
+        CU(c->rtSched.reserve(64 + 4 * kMaxCopyBands), "scheduler alloc");
+        CU(cudaMemsetAsync(c->rtSched.p, 0, 64 + 4 * kMaxCopyBands, c->stream), "scheduler clear");
     }
     a.sched = c->rtSched.as<unsigned>();
+    a.bandDone = bandTileRows > 0 ? c->rtSched.as<unsigned>() + 16 : nullptr;
+    a.bandTileRows = bandTileRows > 0 ? bandTileRows : 1;
     a.useFilter = c->optRtFilter;
     cudaError_t e = launch_rt_trace_shade(c, a, c->stream);
     if (e == cudaErrorInvalidConfiguration)
@@ -429,6 +433,60 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
         for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->partDone[i], cudaEventDisableTiming), "cudaEventCreate");
     }
     cudaStream_t drawStream = c->stream;
+    if (parts > 1 && !c->memOpsProbed) {  // stream memory operations: cuStreamWaitValue32 through the runtime's loader
+        c->memOpsProbed = true;
+        cudaDriverEntryPointQueryResult qr;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && fn)
+            c->waitValue32 = fn;
+        cudaGetLastError();
+    }
+    if (parts > 1 && c->waitValue32 && c->optRtVariant != 4) {
+        // One launch for the whole band.  The kernel counts finished warp tiles per sub-band (tiles are handed out
+        // in row order); the copy stream waits -- on the GPU, no host involvement -- until a sub-band's count is
+        // complete and copies its rows out while the rest of the frame is still being traced.  The copy engine is
+        // about twice as fast as the tracing at config 3, so with 16 sub-bands it stays right behind the frontier
+        // and only the last sub-band's copy is exposed.
+        typedef int (*WaitFn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+        const int tileRows = (rows + 7) / 8, tilesX = (c->W + 31) / 32;
+        const int perBand = (tileRows + 15) / 16, nb = (tileRows + perBand - 1) / perBand;
+        if (!c->rtSched.p) {
+            CU(c->rtSched.reserve(64 + 4 * kMaxCopyBands), "scheduler alloc");
+            CU(cudaMemsetAsync(c->rtSched.p, 0, 64 + 4 * kMaxCopyBands, drawStream), "scheduler clear");
+        }
+        unsigned* done = c->rtSched.as<unsigned>() + 16;
+        CU(cudaMemsetAsync(done, 0, 4 * kMaxCopyBands, drawStream), "band counters clear");
+        CU(cudaEventRecord(c->partDone[0], drawStream), "cudaEventRecord");
+        CU(cudaStreamWaitEvent(c->copyStream, c->partDone[0], 0), "cudaStreamWaitEvent");
+        if (int rc = rt_launch_band(c, y0, y1, needCol ? c->colours.as<float>() : nullptr,
+                                    clo ? c->closest.as<b2r_intersection>() : nullptr,
+                                    needFocal ? c->focal.as<float>() : nullptr, fused ? c->surface.as<uint32_t>() : nullptr, perBand))
+            return rc;
+        c->stream = c->copyStream;  // copy_rows_out issues on c->stream
+        int rc = 0;
+        for (int b = 0; b < nb && !rc; ++b) {
+            const int t0 = b * perBand, t1 = (b + 1) * perBand < tileRows ? (b + 1) * perBand : tileRows;
+            const int a0 = y0 + t0 * 8, a1 = b == nb - 1 ? y1 : y0 + t1 * 8;
+            const unsigned want = (unsigned)(t1 - t0) * (unsigned)tilesX * 8u;
+            if (reinterpret_cast<WaitFn>(c->waitValue32)(c->copyStream, (unsigned long long)(uintptr_t)(done + b), want,
+                                                         0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+                c->stream = drawStream;
+                return fail(c, B2R_E_CUDA, "cuStreamWaitValue32 failed");
+            }
+            rc = copy_rows_out(c, surface, c->surface.p, a0, a1, 4);  // (depth of field never gets here: parts == 1)
+            if (!rc) rc = copy_rows_out(c, col, c->colours.p, a0, a1, 12);
+            if (!rc) rc = copy_rows_out(c, clo, c->closest.p, a0, a1, 20);
+            if (!rc) rc = copy_rows_out(c, foc, c->focal.p, a0, a1, 4);
+        }
+        c->stream = drawStream;
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(c->copyStream), "raytracer draw (copies)");
+        CU(cudaStreamSynchronize(c->stream), "raytracer draw");
+        c->coloursValid = needCol;
+        c->surfaceValid = surface && y0 == 0 && y1 == c->H;
+        return B2R_OK;
+    }
     // Only the last sub-band's copy is exposed (the others overlap the next sub-band's tracing), so the sub-bands
     // shrink towards the end; cuts fall on multiples of the 8-row tile height.
     static const int kCut4[5] = {0, 32, 60, 84, 100}, kCut2[3] = {0, 64, 100};

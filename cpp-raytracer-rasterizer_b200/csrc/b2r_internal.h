@@ -73,6 +73,9 @@ struct RtLaunch {
     float* focal;                       // may be null
     uint32_t* surface;                  // may be null: the resolved XRGB surface (only without depth of field)
     unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
+    unsigned* bandDone;  // may be null: per sub-band, the number of finished warp tiles (host-buffer draw: the copy
+                         // stream waits on these words and copies a sub-band out while the kernel is still tracing)
+    int bandTileRows;    // tile rows (8 pixel rows each) per sub-band
     unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
     int batch;         // warp tiles per scheduler fetch (set by the launcher)
     int useFilter;
@@ -177,7 +180,9 @@ struct Ctx {
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
     DevBuf subScratch;  // staging of the sub-stage entry points
-    DevBuf rtSched;   // raytracer: warp-tile scheduler words (RtLaunch::sched)
+    DevBuf rtSched;   // raytracer: warp-tile scheduler words (RtLaunch::sched), then the band counters (::bandDone)
+    void* waitValue32 = nullptr;  // cuStreamWaitValue32 when the driver offers stream memory operations
+    bool memOpsProbed = false;
     DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
     size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
     void* rasKeysCleanPtr = nullptr;

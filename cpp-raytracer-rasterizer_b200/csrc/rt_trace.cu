@@ -455,7 +455,18 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
         const int wx0 = tx * kTileW + (sub & 3) * 8, wy0 = a.y0 + ty * kTileH + (sub >> 2) * 4;
         const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
         const bool inside = x < a.W && y < a.y1;  // lanes outside stay for the warp collectives
-        if (!__any_sync(kFull, inside)) continue;
+        // Host-buffer draws copy finished row bands out while later ones are still being traced: count this warp
+        // tile as finished once its stores are visible device-wide.
+        auto signal_done = [&]() {
+            if (!a.bandDone) return;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(a.bandDone + ty / a.bandTileRows, 1u);
+        };
+        if (!__any_sync(kFull, inside)) {
+            signal_done();
+            continue;
+        }
 
         // tile-level candidate masks for the primary rays of all sub-samples
         {
@@ -710,6 +721,7 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
             // CalculateDOF without depth of field + PutPixelSDL (:643-651), fused: no second pass over the colours
             if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(avg.x, avg.y, avg.z) : 0u;
         }
+        signal_done();
     }
 
     // The last CTA of the grid to run out of tiles re-arms the scheduler for the next launch (every other CTA

@@ -55,6 +55,32 @@ def test_rt_idempotent_and_band_invariant_4k(pkg, rt4k):
     assert 0.0 <= full["pixelColours"].min() and full["pixelColours"].max() < 4.0
 
 
+def test_host_frame_copy_overlap_4k(pkg, rt4k):
+    """Config 3 through the host-buffer ABI: row bands are copied out while the kernel is still tracing later rows
+    (stream wait-value operations; variant 4 = one launch per sub-band).  Every pass must equal the frame the
+    device-resident call leaves in HBM, bit for bit."""
+    import torch
+    fp = pkg.default_frame_params(0, W, H)
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    rt4k.set_frame(fp)
+    dev = torch.device("cuda:0")
+    surf = torch.zeros((H, W), dtype=torch.int32, device=dev)
+    col = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+    rt4k.rt_frame_device_async(0, H, surf.data_ptr(), col.data_ptr())
+    rt4k.synchronize()
+    want_surf = surf.cpu().numpy().view(np.uint32)
+    want_col = col.cpu().numpy()
+    for variant in (0, 4, 0):
+        rt4k.set_option(pkg.capi.OPT_RT_VARIANT, variant)
+        for _ in range(3):
+            host = np.full((H, W), 0xDEADBEEF, np.uint32)
+            rt4k.rt_frame(host)
+            assert np.array_equal(host, want_surf), variant
+        out = rt4k.rt_draw(closest=False, focal=False)
+        assert np.array_equal(bits(out["pixelColours"]), bits(want_col)), variant
+    rt4k.set_option(pkg.capi.OPT_RT_VARIANT, 0)
+
+
 def test_resolve_rules_4k(pkg, rt4k):
     """PutPixelSDL: Uint8(clamp(255*c,0,255)) by truncation, 1-pixel border untouched (SDLauxiliary.h:70-81, raytracer.cpp:618-620)."""
     rt4k.set_frame(pkg.default_frame_params(0, W, H))
