@@ -47,7 +47,7 @@ def test_rt_idempotent_and_band_invariant_4k(pkg, rt4k):
     full = rt4k.rt_draw(closest=False)
     again = rt4k.rt_draw(closest=False)
     assert np.array_equal(bits(full["pixelColours"]), bits(again["pixelColours"]))
-    for y0, y1 in ((0, 270), (1890, 2160), (1001, 1013)):  # 8-GPU bands and a ragged one
+    for y0, y1 in ((0, 270), (1890, 2160), (1001, 1013), (3, 1238)):  # 8-GPU bands and ragged ones
         part = rt4k.rt_draw(y0, y1, closest=False)
         assert np.array_equal(bits(part["pixelColours"][y0:y1]), bits(full["pixelColours"][y0:y1]))
         assert np.array_equal(bits(part["focalDistances"][y0:y1]), bits(full["focalDistances"][y0:y1]))
