@@ -180,6 +180,12 @@ struct Ctx {
     // rasteriser intermediates
     DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
     DevBuf subScratch;  // staging of the sub-stage entry points
+    struct KernelInfo {
+        const void* fn;
+        size_t smem;
+        int perSM;
+    };
+    std::vector<KernelInfo> rtKernelCache;  // raytracer variants already configured (shared-memory opt-in, CTAs/SM)
     DevBuf rtSched;   // raytracer: warp-tile scheduler words (RtLaunch::sched), then the band counters (::bandDone)
     void* waitValue32 = nullptr;  // cuStreamWaitValue32 when the driver offers stream memory operations
     bool memOpsProbed = false;

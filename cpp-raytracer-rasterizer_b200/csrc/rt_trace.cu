@@ -761,18 +761,28 @@ static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident, bool cach
     return quads * 16 + (size_t)(kThreads / 32) * ((nChunks + 1) / 2 * 2) * 8 + (cache ? rt_cache_bytes(T, nO) : 0) + 16;
 }
 
+constexpr int kMaxDynamicSmem = 200 * 1024;  // launch_rt_trace_shade refuses scenes that need more
+
 template <bool RESIDENT, bool TILECULL, bool SINGLE = false, bool ONE = false>
 static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
     auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true, SINGLE, ONE>
                                        : rt_trace_shade_kernel<RESIDENT, TILECULL, true, false, SINGLE, ONE>)
                             : (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, false, true, SINGLE, ONE>
                                        : rt_trace_shade_kernel<RESIDENT, TILECULL, false, false, SINGLE, ONE>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int perSM = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (perSM < 1) perSM = 1;
+    // shared-memory opt-in and occupancy: once per (variant, shared-memory size) and context
+    int perSM = 0;
+    for (const auto& k : c->rtKernelCache)
+        if (k.fn == (const void*)kern && k.smem == smem) perSM = k.perSM;
+    cudaError_t e;
+    if (perSM == 0) {
+        // the opt-in is a per-function, per-device setting shared by every context: always the same upper bound
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynamicSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, kThreads, smem);
+        if (e != cudaSuccess) return e;
+        if (perSM < 1) perSM = 1;
+        c->rtKernelCache.push_back({(const void*)kern, smem, perSM});
+    }
     int grid = c->smCount * perSM;
     if (grid > a.numTiles) grid = a.numTiles;
     if (grid < 1) return cudaSuccess;
@@ -811,7 +821,7 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
         return c->optRtVariant == 1 ? launch_variant<true, false>(c, a, smemRes, s) : launch_variant<true, true>(c, a, smemRes, s);
     }
     const size_t smem = rt_smem_bytes(a.T, f.nOrigins, f.nLights, false, cache);
-    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;  // > ~100k triangles: reported as B2R_E_UNSUPPORTED
+    if (smem > (size_t)kMaxDynamicSmem) return cudaErrorInvalidConfiguration;  // > ~100k triangles: reported as B2R_E_UNSUPPORTED
     const size_t pairs = (size_t)f.nOrigins * (size_t)a.T;
     cudaError_t e;
     if ((e = c->rtX.reserve(pairs * 32 + 64)) != cudaSuccess) return e;
