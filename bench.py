@@ -321,16 +321,18 @@ def run_gpu_arm(args, pkg):
         bms = float(t.item()) / args.steps
         extra["band_split"] = {"ms_per_frame": bms, "value": rays / (bms * 1e-3) / 1e6, "unit": "Mrays/s",
                                "scaling": "strong", "collective": "nccl all_gather of 32-bit surface bands"}
-        # fused variant: the resolve kernel stores each pixel straight into every rank's surface over NVLink
-        # (peer-mapped buffers), so the band exchange is part of the kernel; a 4-byte all-reduce orders the frames
+        # fused variant: the trace kernel stores each resolved pixel straight into every rank's surface over NVLink
+        # (peer-mapped buffers) and the ranks take interleaved tile rows, so the exchange is part of the one kernel
+        # and the load is even; a 4-byte all-reduce orders the frames
         mine, handle = ctx.shared_alloc(npx * 4)
         handles = [None] * world
         dist.all_gather_object(handles, handle)
         ptrs = [mine if r == rank else ctx.shared_open(handles[r]) for r in range(world)]
         tick = torch.zeros(1, dtype=torch.int32, device=dev)
+        order = [mine] + [p for r, p in enumerate(ptrs) if r != rank]
         def frame_band_fused():
-            ctx.rt_draw_device_async(y0, y1, d_col.data_ptr())
-            ctx.resolve_surface_multi_device_async(y0, y1, d_col.data_ptr(), 0, ptrs)
+            # ONE kernel per rank: traces its interleaved tile rows and stores every pixel into all ranks' surfaces
+            ctx.rt_frame_split_device_async(rank, world, order)
             with torch.cuda.stream(stream):
                 dist.all_reduce(tick)
         fms = timed_loop(frame_band_fused, args.steps, args.warmup)
@@ -339,7 +341,7 @@ def run_gpu_arm(args, pkg):
         fms = float(t.item()) / args.steps
         extra["band_split_fused"] = {"ms_per_frame": fms, "value": rays / (fms * 1e-3) / 1e6, "unit": "Mrays/s",
                                      "scaling": "strong",
-                                     "exchange": "resolve kernel stores into peer-mapped surfaces (CUDA IPC over NVLink)"}
+                                     "exchange": "trace kernel stores into peer-mapped surfaces (CUDA IPC over NVLink), tile rows interleaved across ranks"}
         barrier()
         for r in range(world):
             if r != rank:

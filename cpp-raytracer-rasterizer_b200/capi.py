@@ -93,7 +93,7 @@ SYMBOLS = [
     "b2r_set_triangles", "b2r_set_culled", "b2r_set_frame", "b2r_rt_draw", "b2r_ras_draw", "b2r_ras_cull",
     "b2r_resolve_surface", "b2r_resolve_bgr8", "b2r_bmp_payload_bytes", "b2r_write_bmp", "b2r_rt_frame",
     "b2r_ras_frame", "b2r_set_stream", "b2r_get_stream", "b2r_synchronize", "b2r_rt_draw_device_async",
-    "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_rt_frame_device_async", "b2r_ras_frame_device_async", "b2r_launch_count", "b2r_get_stats",
+    "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_rt_frame_device_async", "b2r_ras_frame_device_async", "b2r_rt_frame_split_device_async", "b2r_launch_count", "b2r_get_stats",
     "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_scene_cornell_box",
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
     "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
@@ -143,6 +143,7 @@ def load_library():
     lib.b2r_resolve_surface_device_async.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.b2r_rt_frame_device_async.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.b2r_ras_frame_device_async.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.b2r_rt_frame_split_device_async.argtypes = [vp, i32, i32, C.POINTER(vp), i32, vp, vp, vp]
     lib.b2r_shared_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
     lib.b2r_shared_free.argtypes = [vp, vp]
     lib.b2r_shared_open.argtypes = [vp, vp, C.POINTER(vp)]
@@ -314,6 +315,12 @@ class Context:
         self._chk(self.lib.b2r_ras_draw_device_async(self.handle, y0, y1, C.c_void_p(d_depth),
                                                      C.c_void_p(d_colours), C.c_void_p(d_focal),
                                                      C.c_void_p(d_winner)))
+
+    def rt_frame_split_device_async(self, part, nparts, surfaces, d_colours=0, d_closest=0, d_focal=0):
+        """Tile rows part, part+nparts, ... of the frame, every pixel stored into all `surfaces` (device addresses)."""
+        arr = (C.c_void_p * len(surfaces))(*surfaces)
+        self._chk(self.lib.b2r_rt_frame_split_device_async(self.handle, part, nparts, arr, len(surfaces),
+                                                           C.c_void_p(d_colours), C.c_void_p(d_closest), C.c_void_p(d_focal)))
 
     def ras_frame_device_async(self, y0, y1, d_surface, d_depth=0, d_colours=0, d_focal=0, d_winner=0):
         self._chk(self.lib.b2r_ras_frame_device_async(self.handle, y0, y1, C.c_void_p(d_surface), C.c_void_p(d_depth),

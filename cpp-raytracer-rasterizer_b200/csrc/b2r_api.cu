@@ -351,8 +351,15 @@ int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds) {
 // ---- raytracer ------------------------------------------------------------------
 constexpr int kMaxCopyBands = 32;
 
+// Optional extras of one raytracer launch: further surface copies and the tile-row interleave of a multi-GPU split.
+struct RtSplit {
+    uint32_t* const* peers = nullptr;
+    int nPeers = 0;
+    int stride = 1, offset = 0;
+};
+
 static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
-                          uint32_t* d_surf = nullptr, int bandTileRows = 0) {
+                          uint32_t* d_surf = nullptr, int bandTileRows = 0, const RtSplit* split = nullptr) {
     c->lastDraw = 0;
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
@@ -381,7 +388,16 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.y0 = y0;
     a.y1 = y1;
     a.tilesX = (c->W + 31) / 32;
-    a.numTiles = a.tilesX * ((y1 - y0 + 7) / 8);
+    a.tileRowStride = split ? split->stride : 1;
+    a.tileRowOffset = split ? split->offset : 0;
+    a.nPeerSurfaces = split ? split->nPeers : 0;
+    for (int i = 0; i < B2R_MAX_PEERS - 1; ++i) a.peerSurface[i] = (split && i < split->nPeers) ? split->peers[i] : nullptr;
+    {
+        const int tileRows = (y1 - y0 + 7) / 8;  // of the band; this launch takes every stride-th one
+        const int mine = tileRows > a.tileRowOffset ? (tileRows - a.tileRowOffset + a.tileRowStride - 1) / a.tileRowStride : 0;
+        a.numTiles = a.tilesX * mine;
+        if (mine == 0) return B2R_OK;
+    }
     a.colours = d_col;
     a.closest = d_clo;
     a.focal = d_foc;
@@ -542,6 +558,25 @@ int b2r_rt_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface,
     if (int rc = rt_launch_band(c, y0, y1, d_col, d_clo, d_foc)) return rc;
     CU(launch_resolve_surface(c, y0, y1, d_col, d_foc, d_surface, c->stream), "resolve_surface_kernel");
     return B2R_OK;
+}
+
+int b2r_rt_frame_split_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t* const* d_surfaces, int n, float* d_col,
+                                    b2r_intersection* d_clo, float* d_foc) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (nparts < 1 || part < 0 || part >= nparts || !d_surfaces || n < 1 || n > B2R_MAX_PEERS)
+        return fail(c, B2R_E_INVALID, "rt_frame_split: bad arguments (0 <= part < nparts, 1..8 destination surfaces)");
+    for (int i = 0; i < n; ++i)
+        if (!d_surfaces[i]) return fail(c, B2R_E_INVALID, "rt_frame_split: null destination");
+    if (c->params.dofEnabled)
+        return fail(c, B2R_E_UNSUPPORTED, "rt_frame_split: depth of field needs the neighbouring rows; draw, exchange pixelColours, then resolve");
+    if (int rc = reset_stats(c)) return rc;
+    RtSplit sp;
+    sp.peers = d_surfaces + 1;
+    sp.nPeers = n - 1;
+    sp.stride = nparts;
+    sp.offset = part;
+    return rt_launch_band(c, 0, c->H, d_col, d_clo, d_foc, d_surfaces[0], 0, &sp);
 }
 
 int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* clo, float* foc) {

@@ -72,6 +72,9 @@ struct RtLaunch {
     b2r_intersection* closest;          // may be null
     float* focal;                       // may be null
     uint32_t* surface;                  // may be null: the resolved XRGB surface (only without depth of field)
+    uint32_t* peerSurface[B2R_MAX_PEERS - 1];  // further copies of the surface, e.g. peer-mapped buffers of other GPUs
+    int nPeerSurfaces;                  // (single-frame multi-GPU split: the exchange is part of the trace kernel)
+    int tileRowStride, tileRowOffset;   // this launch draws tile rows offset, offset + stride, ... (1, 0 = all)
     unsigned long long* stats;          // device counters (B2R_STAT_*), null when stats are off
     unsigned* bandDone;  // may be null: per sub-band, the number of finished warp tiles (host-buffer draw: the copy
                          // stream waits on these words and copies a sub-band out while the kernel is still tracing)

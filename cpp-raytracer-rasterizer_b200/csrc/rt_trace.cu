@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
     for (int wt = base; wt < min(base + batch, numWarpTiles); ++wt) {
         const int tile = wt >> 3, sub = wt & 7;
         const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
-        const int wx0 = tx * kTileW + (sub & 3) * 8, wy0 = a.y0 + ty * kTileH + (sub >> 2) * 4;
+        const int wx0 = tx * kTileW + (sub & 3) * 8,
+                  wy0 = a.y0 + (ty * a.tileRowStride + a.tileRowOffset) * kTileH + (sub >> 2) * 4;
         const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
         const bool inside = x < a.W && y < a.y1;  // lanes outside stay for the warp collectives
         // Host-buffer draws copy finished row bands out while later ones are still being traced: count this warp
@@ -719,7 +720,11 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
             }
             if (a.focal) a.focal[idx] = ps.focal;
             // CalculateDOF without depth of field + PutPixelSDL (:643-651), fused: no second pass over the colours
-            if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(avg.x, avg.y, avg.z) : 0u;
+            if (a.surface) {
+                const uint32_t px = inside_border(x, y, a.W, a.H) ? pack_xrgb(avg.x, avg.y, avg.z) : 0u;
+                a.surface[idx] = px;
+                for (int d = 0; d < a.nPeerSurfaces; ++d) a.peerSurface[d][idx] = px;  // other GPUs' copies, over NVLink
+            }
         }
         signal_done();
     }

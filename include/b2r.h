@@ -168,6 +168,15 @@ int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_depthBuffer
  * from d_pixelColours / d_focalDistances (required), whose neighbouring rows must already be up to date. */
 int b2r_rt_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_pixelColours,
                               b2r_intersection* d_closestIntersections, float* d_focalDistances);
+/* One frame split over `nparts` GPUs with the exchange inside the trace kernel: this call draws tile rows (8 pixel
+ * rows) part, part + nparts, ... of the whole frame -- interleaved, so every part carries the same mix of cheap and
+ * expensive rows -- and stores each resolved pixel into all n surfaces: d_surfaces[0] is normally the local one, the
+ * others peer-mapped buffers of the other GPUs (b2r_shared_open), written over NVLink.  After every part has run
+ * (and the caller has ordered the frames, e.g. with a barrier) each surface holds the full frame.  Not available
+ * with depth of field (B2R_E_UNSUPPORTED).  d_pixelColours etc. are optional full-frame arrays (local rows only). */
+int b2r_rt_frame_split_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t* const* d_surfaces, int n,
+                                    float* d_pixelColours, b2r_intersection* d_closestIntersections,
+                                    float* d_focalDistances);
 int b2r_ras_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_depthBuffer,
                                float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
 /* Resolve rows [y0,y1) of d_pixelColours (+ d_focalDistances when DOF is on) into d_surface. */

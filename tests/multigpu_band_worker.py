@@ -55,6 +55,19 @@ def main():
     ctx.synchronize()
     assert torch.equal(tmp, ref_surf), f"rank {rank}: fused band exchange differs from the single-GPU frame"
 
+    # --- exchange inside the trace kernel: interleaved tile rows, every pixel stored into every rank's surface
+    dist.barrier()
+    ctx.copy_device_async(mine, torch.full((h, w), -1, dtype=torch.int32, device=dev).data_ptr(), w * h * 4)
+    ctx.synchronize()
+    dist.barrier()
+    ctx.rt_frame_split_device_async(rank, world, [mine] + [p for r, p in enumerate(ptrs) if r != rank])
+    ctx.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ctx.copy_device_async(tmp.data_ptr(), mine, w * h * 4)
+    ctx.synchronize()
+    assert torch.equal(tmp, ref_surf), f"rank {rank}: split frame (trace kernel + peer stores) differs from the single-GPU frame"
+
     # --- NCCL variant (parallel.gather_bands)
     surf = torch.zeros((h, w), dtype=torch.int32, device=dev)
     ctx.resolve_surface_device_async(y0, y1, col.data_ptr(), 0, surf.data_ptr())

@@ -108,3 +108,34 @@ def test_fused_frame_device_equals_draw_then_resolve(pkg, which, dof, aa):
         with pytest.raises(pkg.B2RError):
             frame(0, h, got.data_ptr())
     ctx.close()
+
+
+@pytest.mark.parametrize("nparts", [1, 3, 8])
+def test_split_frame_interleaved_tile_rows(pkg, nparts):
+    """b2r_rt_frame_split_device_async: part p draws tile rows p, p+nparts, ... and stores every pixel into all
+    destination surfaces; after all parts ran, every surface equals the frame one launch draws (on several GPUs the
+    extra destinations are peer-mapped, tests/test_multigpu.py)."""
+    import torch
+    w, h = 200, 141  # ragged last tile row
+    dev = torch.device("cuda:0")
+    fp = pkg.default_frame_params(0, w, h)
+    fp.aaEnabled, fp.aaSamples = 1, 2
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(pkg.cornell_box())
+    ctx.set_frame(fp)
+    ref = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    col_ref = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    ctx.rt_frame_device_async(0, h, ref.data_ptr(), col_ref.data_ptr())
+    a = torch.full((h, w), -1, dtype=torch.int32, device=dev)
+    b = torch.full((h, w), -1, dtype=torch.int32, device=dev)
+    col = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    for part in range(nparts):
+        ctx.rt_frame_split_device_async(part, nparts, [a.data_ptr(), b.data_ptr()], col.data_ptr())
+    ctx.synchronize()
+    assert torch.equal(a, ref) and torch.equal(b, ref)
+    assert torch.equal(col.view(torch.int32), col_ref.view(torch.int32))
+    fp.dofEnabled = 1
+    ctx.set_frame(fp)
+    with pytest.raises(pkg.B2RError):
+        ctx.rt_frame_split_device_async(0, 2, [a.data_ptr()])
+    ctx.close()
