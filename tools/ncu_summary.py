@@ -45,18 +45,25 @@ def main():
             if m in hdr:
                 k["metrics"][m] = [row[hdr.index(m)], units[hdr.index(m)]]
         kernels.append(k)
-    src = ncu_csv(rep, "source")
-    # the source page of a multi-kernel report repeats "Kernel Name" blocks; take them in order
-    blocks, cur = [], None
-    for r in src:
-        if r and r[0] == "Kernel Name":
-            cur = {"name": r[1], "hdr": None, "rows": []}
-            blocks.append(cur)
-        elif cur is not None and cur["hdr"] is None:
-            cur["hdr"] = r
-        elif cur is not None:
-            cur["rows"].append(r)
-    for k, b in zip(kernels, blocks):
+    import re
+    for k in kernels:
+        # the source page holds one kernel at a time: select it by (escaped) base name
+        base = re.sub(r"^(void )?(\w+::)*", "", k["kernel"]).split("(")[0].split("<")[0]
+        src = ncu_csv(rep, "source", ("-k", "regex:" + base))
+        b = {"hdr": None, "rows": []}
+        seen = 0
+        for r in src:
+            if r and r[0] == "Kernel Name":
+                seen += 1
+                if seen > 1:  # further launches of the same kernel: the first one is enough
+                    break
+                continue
+            if b["hdr"] is None:
+                b["hdr"] = r
+            else:
+                b["rows"].append(r)
+        if not b["hdr"]:
+            continue
         h = b["hdr"]
         ia, isrc = h.index("Instructions Executed"), h.index("Source")
         stall_cols = [(i, c) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]

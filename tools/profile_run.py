@@ -17,8 +17,7 @@ if which == "rt":
     col = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
     surf = torch.empty((H, W), dtype=torch.int32, device=dev)
     for _ in range(3):
-        ctx.rt_draw_device_async(0, H, col.data_ptr())
-        ctx.resolve_surface_device_async(0, H, col.data_ptr(), 0, surf.data_ptr())
+        ctx.rt_frame_device_async(0, H, surf.data_ptr(), col.data_ptr())
     ctx.synchronize()
 elif which == "ras30":
     ctx = pkg.Context(W, H)
