@@ -179,6 +179,7 @@ def load_library():
 OPT_RT_FILTER = 0        # 1 (default): conservative FMA filter in front of the exact test; 0: exact test on every pair
 OPT_RT_VARIANT = 1       # kernel variant selector
 OPT_RAS_VARIANT = 2
+OPT_DOF_VARIANT = 3
 
 
 class B2RError(RuntimeError):

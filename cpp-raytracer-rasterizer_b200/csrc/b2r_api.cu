@@ -307,6 +307,7 @@ int b2r_set_option(b2r_ctx* ctx, int option, int value) {
         case B2R_OPT_RT_FILTER: c->optRtFilter = value ? 1 : 0; return B2R_OK;
         case B2R_OPT_RT_VARIANT: c->optRtVariant = value; return B2R_OK;
         case B2R_OPT_RAS_VARIANT: c->optRasVariant = value; return B2R_OK;
+        case B2R_OPT_DOF_VARIANT: c->optDofVariant = value; return B2R_OK;
     }
     return fail(c, B2R_E_INVALID, "unknown option");
 }

@@ -202,7 +202,7 @@ struct Ctx {
     DevBuf stats;
     bool statsOn = false;
     unsigned long long launches = 0;
-    int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0;
+    int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0, optDofVariant = 0;
     int lastDraw = -1;  // 0 raytracer, 1 rasteriser
     // what the context's own buffers hold after the last host-buffer draw: the fused raytracer frame may leave only
     // the resolved surface (no pixelColours); b2r_resolve_* then start from it

@@ -5,6 +5,8 @@
 // One thread per pixel; HBM-bound (12-16 B read, 4 B written per pixel).
 // Also: the FP32 FFMA throughput microbenchmark that gives the raytracer's
 // roofline denominator (MEASURED_PEAKS.json has no FP32 entry).
+#include <type_traits>
+
 #include "b2r_internal.h"
 #include "exact.cuh"
 #include "pixel_pack.cuh"
@@ -61,12 +63,104 @@ __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __res
         if (d < dst.n) dst.p[d][o] = out;
 }
 
+// ---- depth of field with the reference's 8x8 window (DOF_KERNEL_SIZE 8, raytracer.cpp:45) -------------------
+// The generic kernel above issues 192 scalar loads per pixel and is bound by the load/store unit.  Here a CTA of
+// 256 threads resolves a 128 x 8 pixel tile: the (128+8) x (8+7) window of pixelColours is staged once in shared
+// memory as three channel planes (out-of-array taps as 0: adding 0*w leaves the running sum unchanged, it starts
+// at +0 and never becomes -0, so this equals the reference's skipped taps), every thread resolves 4 adjacent pixels
+// and reads each window row with three 128-bit loads per channel.  Per pixel and channel the 64 products are
+// added in the reference's order (z rows outer, z2 columns inner, :626-639), unfused.
+constexpr int kDofTileW = 128, kDofTileH = 8, kDofCols = kDofTileW + 8, kDofRows = kDofTileH + 7;
+constexpr int kDofPlane = kDofCols * kDofRows + 4;  // +4 floats: planes start on different banks
+
+__global__ void __launch_bounds__(256) resolve_dof8_kernel(const float* __restrict__ colours,
+                                                           const float* __restrict__ focal, int W, int H, int y0,
+                                                           int y1, const SurfDst dst) {
+    __shared__ __align__(16) float tile[3 * kDofPlane];
+    const int tx0 = blockIdx.x * kDofTileW, ty0 = y0 + blockIdx.y * kDofTileH;
+    const long long n = (long long)W * H;
+    // stage: window row r <-> frame row ty0 - 4 + r, window column c <-> frame column tx0 - 4 + c, flattened like
+    // the reference's (y+z)*W + (x+z2): columns beyond a row's ends continue into the neighbouring rows
+    // (all loads of a thread are issued before its first store, so their latencies overlap)
+    constexpr int kElems = 3 * kDofCols * kDofRows, kPerThread = (kElems + 255) / 256;
+    float stage[kPerThread];
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        const int e = threadIdx.x + 256 * i;
+        const int r = e / (3 * kDofCols), f = e - r * (3 * kDofCols);
+        const long long q = (long long)(ty0 - 4 + r) * W + (tx0 - 4) + f / 3;
+        stage[i] = (e < kElems && q >= 0 && q < n) ? colours[3 * q + (f % 3)] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < kPerThread; ++i) {
+        const int e = threadIdx.x + 256 * i;
+        const int r = e / (3 * kDofCols), f = e - r * (3 * kDofCols);
+        if (e < kElems) tile[(f % 3) * kDofPlane + r * kDofCols + f / 3] = stage[i];
+    }
+    __syncthreads();
+    const int lx = (threadIdx.x & 31) * 4, ly = threadIdx.x >> 5;  // 32 x 8 threads, 4 pixels each
+    const int y = ty0 + ly, xb = tx0 + lx;
+    if (y >= y1) return;
+    float wC[4], wO[4];
+    bool live[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = xb + p;
+        live[p] = x < W && inside_border(x, y, W, H);
+        float a = live[p] ? fabsf(focal[(long long)y * W + x]) : 0.f;
+        const float m = (1.0f < a) ? 1.0f : a;                 // std::min(abs(fd), 1.0f)
+        wC[p] = xsub(1.0f, xmul(m, xdiv(xsub(64.0f, 1.0f), 64.0f)));  // :632
+        wO[p] = xmul(m, xdiv(1.0f, 64.0f));                           // :634
+    }
+    float acc[4][3];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) acc[p][0] = acc[p][1] = acc[p][2] = 0.f;
+    // one window row: frame row y - 4 + z = window row ly + z; CENTRE marks the row that holds the centre tap
+    auto add_row = [&](int z, auto centre) {
+        constexpr bool CENTRE = decltype(centre)::value;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float4* row = reinterpret_cast<const float4*>(tile + ch * kDofPlane + (ly + z) * kDofCols + lx);
+            const float4 v0 = row[0], v1 = row[1], v2 = row[2];
+            const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int z2 = 0; z2 < 8; ++z2) {  // frame column x - 4 + z2 = window column lx + p + z2
+                    const float w = (CENTRE && z2 == 4) ? wC[p] : wO[p];
+                    acc[p][ch] = xadd(acc[p][ch], xmul(v[p + z2], w));  // :637
+                }
+        }
+    };
+#pragma unroll 1
+    for (int z = 0; z < 4; ++z) add_row(z, std::false_type{});
+    add_row(4, std::true_type{});
+#pragma unroll 1
+    for (int z = 5; z < 8; ++z) add_row(z, std::false_type{});
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int x = xb + p;
+        if (x >= W) continue;
+        const uint32_t out = live[p] ? pack_xrgb(acc[p][0], acc[p][1], acc[p][2]) : 0u;
+        const size_t o = (size_t)y * W + x;
+#pragma unroll
+        for (int d = 0; d < B2R_MAX_PEERS; ++d)
+            if (d < dst.n) dst.p[d][o] = out;
+    }
+}
+
 cudaError_t launch_resolve_surface_multi(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
                                          uint32_t* const* d_surfaces, int n, cudaStream_t s) {
     if (y1 <= y0 || n <= 0) return cudaSuccess;
     SurfDst dst;
     dst.n = n;
     for (int d = 0; d < B2R_MAX_PEERS; ++d) dst.p[d] = d < n ? d_surfaces[d] : nullptr;
+    if (c->params.dofEnabled && c->params.dofKernelSize == 8 && c->optDofVariant != 1) {
+        dim3 g8((c->W + kDofTileW - 1) / kDofTileW, (y1 - y0 + kDofTileH - 1) / kDofTileH);
+        resolve_dof8_kernel<<<g8, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0, y1, dst);
+        c->launches++;
+        return cudaGetLastError();
+    }
     dim3 grid((c->W + 255) / 256, y1 - y0);
     resolve_surface_kernel<<<grid, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0,
                                                 c->params.dofEnabled ? 1 : 0, c->params.dofKernelSize, dst);

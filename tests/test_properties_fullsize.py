@@ -81,6 +81,20 @@ def test_host_frame_copy_overlap_4k(pkg, rt4k):
     rt4k.set_option(pkg.capi.OPT_RT_VARIANT, 0)
 
 
+def test_dof_kernels_agree_4k(pkg, rt4k):
+    """CalculateDOF with the 8x8 window at 3840x2160: tiled kernel == generic kernel on every pixel."""
+    fp = pkg.default_frame_params(0, W, H)
+    fp.dofEnabled = 1
+    rt4k.set_frame(fp)
+    rt4k.rt_draw(closest=False)
+    tiled = rt4k.resolve_surface()
+    rt4k.set_option(pkg.capi.OPT_DOF_VARIANT, 1)
+    generic = rt4k.resolve_surface()
+    rt4k.set_option(pkg.capi.OPT_DOF_VARIANT, 0)
+    assert np.array_equal(tiled, generic)
+    assert tiled.any()
+
+
 def test_resolve_rules_4k(pkg, rt4k):
     """PutPixelSDL: Uint8(clamp(255*c,0,255)) by truncation, 1-pixel border untouched (SDLauxiliary.h:70-81, raytracer.cpp:618-620)."""
     rt4k.set_frame(pkg.default_frame_params(0, W, H))

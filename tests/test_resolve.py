@@ -139,3 +139,35 @@ def test_split_frame_interleaved_tile_rows(pkg, nparts):
     with pytest.raises(pkg.B2RError):
         ctx.rt_frame_split_device_async(0, 2, [a.data_ptr()])
     ctx.close()
+
+
+@pytest.mark.parametrize("size", [(200, 141), (131, 9), (640, 360)])
+def test_dof_tiled_kernel_equals_generic(pkg, oracle, size):
+    """Depth of field, 8x8 window: the shared-memory tiled kernel (default) against the generic one-thread-per-pixel
+    kernel (B2R_OPT_DOF_VARIANT=1) and the oracle, at sizes with ragged tiles; band by band too (the window reads
+    rows outside the band)."""
+    w, h = size
+    fp = pkg.default_frame_params(0, w, h)
+    fp.dofEnabled = 1
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(pkg.cornell_box())
+    ctx.set_frame(fp)
+    out = ctx.rt_draw()
+    want = oracle.resolve_surface(out["pixelColours"], out["focalDistances"], True, 8)
+    tiled = ctx.resolve_surface()
+    ctx.set_option(pkg.capi.OPT_DOF_VARIANT, 1)
+    generic = ctx.resolve_surface()
+    ctx.set_option(pkg.capi.OPT_DOF_VARIANT, 0)
+    assert np.array_equal(generic, want)
+    assert np.array_equal(tiled, want)
+    import torch
+    dev = torch.device("cuda:0")
+    col = torch.from_numpy(out["pixelColours"]).to(dev)
+    foc = torch.from_numpy(out["focalDistances"]).to(dev)
+    surf = torch.full((h, w), -1, dtype=torch.int32, device=dev)
+    cuts = sorted({0, min(3, h), min(h // 2 + 1, h), h})
+    for y0, y1 in zip(cuts[:-1], cuts[1:]):
+        ctx.resolve_surface_device_async(y0, y1, col.data_ptr(), foc.data_ptr(), surf.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(surf.cpu().numpy().view(np.uint32), want)
+    ctx.close()
