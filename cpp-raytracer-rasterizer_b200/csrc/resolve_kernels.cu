@@ -66,36 +66,39 @@ __global__ void __launch_bounds__(256) resolve_surface_kernel(const float* __res
 // ---- depth of field with the reference's 8x8 window (DOF_KERNEL_SIZE 8, raytracer.cpp:45) -------------------
 // The generic kernel above issues 192 scalar loads per pixel and is bound by the load/store unit.  Here a CTA of
 // 256 threads resolves a 128 x 8 pixel tile: the (128+8) x (8+7) window of pixelColours is staged once in shared
-// memory as three channel planes (out-of-array taps as 0: adding 0*w leaves the running sum unchanged, it starts
-// at +0 and never becomes -0, so this equals the reference's skipped taps), every thread resolves 4 adjacent pixels
-// and reads each window row with three 128-bit loads per channel.  Per pixel and channel the 64 products are
-// added in the reference's order (z rows outer, z2 columns inner, :626-639), unfused.
+// memory exactly as it lies in HBM (rgb interleaved; each window row is one contiguous run of the flattened array,
+// which also reproduces the reference's wrap of out-of-row columns into the neighbouring rows), with 128-bit
+// loads and stores.  Out-of-array taps are staged as 0: adding 0*w leaves the running sum unchanged (it starts at
+// +0 and never becomes -0), which equals the reference's skipped taps.  Every thread resolves 4 adjacent pixels
+// and reads each window row with nine 128-bit shared loads.  Per pixel and channel the 64 products are added in the
+// reference's order (z rows outer, z2 columns inner, :626-639), unfused.  Needs W % 4 == 0 and a 16-byte aligned
+// pixelColours (the launcher falls back to the generic kernel otherwise).
 constexpr int kDofTileW = 128, kDofTileH = 8, kDofCols = kDofTileW + 8, kDofRows = kDofTileH + 7;
-constexpr int kDofPlane = kDofCols * kDofRows + 4;  // +4 floats: planes start on different banks
+constexpr int kDofRowFloats = 3 * kDofCols, kDofRowQuads = kDofRowFloats / 4;
+static_assert(kDofRowFloats % 4 == 0, "window rows are copied in 16-byte pieces");
 
 __global__ void __launch_bounds__(256) resolve_dof8_kernel(const float* __restrict__ colours,
                                                            const float* __restrict__ focal, int W, int H, int y0,
                                                            int y1, const SurfDst dst) {
-    __shared__ __align__(16) float tile[3 * kDofPlane];
+    __shared__ __align__(16) float tile[kDofRows * kDofRowFloats];
     const int tx0 = blockIdx.x * kDofTileW, ty0 = y0 + blockIdx.y * kDofTileH;
-    const long long n = (long long)W * H;
-    // stage: window row r <-> frame row ty0 - 4 + r, window column c <-> frame column tx0 - 4 + c, flattened like
-    // the reference's (y+z)*W + (x+z2): columns beyond a row's ends continue into the neighbouring rows
-    // (all loads of a thread are issued before its first store, so their latencies overlap)
-    constexpr int kElems = 3 * kDofCols * kDofRows, kPerThread = (kElems + 255) / 256;
-    float stage[kPerThread];
+    const long long nFloats = 3LL * W * H;
+    // stage: window row r <-> frame row ty0 - 4 + r, starting at frame column tx0 - 4 (all loads of a thread are
+    // issued before its first store, so their latencies overlap)
+    constexpr int kQuads = kDofRows * kDofRowQuads, kPerThread = (kQuads + 255) / 256;
+    float4 stage[kPerThread];
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
         const int e = threadIdx.x + 256 * i;
-        const int r = e / (3 * kDofCols), f = e - r * (3 * kDofCols);
-        const long long q = (long long)(ty0 - 4 + r) * W + (tx0 - 4) + f / 3;
-        stage[i] = (e < kElems && q >= 0 && q < n) ? colours[3 * q + (f % 3)] : 0.0f;
+        const int r = e / kDofRowQuads, k = e - r * kDofRowQuads;
+        const long long F = 3 * ((long long)(ty0 - 4 + r) * W + (tx0 - 4)) + 4 * k;  // multiple of 4: W % 4 == 0
+        stage[i] = (e < kQuads && F >= 0 && F < nFloats) ? *reinterpret_cast<const float4*>(colours + F)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int i = 0; i < kPerThread; ++i) {
         const int e = threadIdx.x + 256 * i;
-        const int r = e / (3 * kDofCols), f = e - r * (3 * kDofCols);
-        if (e < kElems) tile[(f % 3) * kDofPlane + r * kDofCols + f / 3] = stage[i];
+        if (e < kQuads) reinterpret_cast<float4*>(tile)[e] = stage[i];
     }
     __syncthreads();
     const int lx = (threadIdx.x & 31) * 4, ly = threadIdx.x >> 5;  // 32 x 8 threads, 4 pixels each
@@ -118,19 +121,22 @@ __global__ void __launch_bounds__(256) resolve_dof8_kernel(const float* __restri
     // one window row: frame row y - 4 + z = window row ly + z; CENTRE marks the row that holds the centre tap
     auto add_row = [&](int z, auto centre) {
         constexpr bool CENTRE = decltype(centre)::value;
+        const float4* row = reinterpret_cast<const float4*>(tile + (ly + z) * kDofRowFloats + 3 * lx);
+        float v[36];  // 12 window columns x rgb
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float4* row = reinterpret_cast<const float4*>(tile + ch * kDofPlane + (ly + z) * kDofCols + lx);
-            const float4 v0 = row[0], v1 = row[1], v2 = row[2];
-            const float v[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+        for (int j = 0; j < 9; ++j) {
+            const float4 t = row[j];
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
                 for (int z2 = 0; z2 < 8; ++z2) {  // frame column x - 4 + z2 = window column lx + p + z2
                     const float w = (CENTRE && z2 == 4) ? wC[p] : wO[p];
-                    acc[p][ch] = xadd(acc[p][ch], xmul(v[p + z2], w));  // :637
+                    acc[p][ch] = xadd(acc[p][ch], xmul(v[3 * (p + z2) + ch], w));  // :637
                 }
-        }
     };
 #pragma unroll 1
     for (int z = 0; z < 4; ++z) add_row(z, std::false_type{});
@@ -155,7 +161,8 @@ cudaError_t launch_resolve_surface_multi(Ctx* c, int y0, int y1, const float* d_
     SurfDst dst;
     dst.n = n;
     for (int d = 0; d < B2R_MAX_PEERS; ++d) dst.p[d] = d < n ? d_surfaces[d] : nullptr;
-    if (c->params.dofEnabled && c->params.dofKernelSize == 8 && c->optDofVariant != 1) {
+    if (c->params.dofEnabled && c->params.dofKernelSize == 8 && c->optDofVariant != 1 && c->W % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(d_colours) & 15u) == 0) {
         dim3 g8((c->W + kDofTileW - 1) / kDofTileW, (y1 - y0 + kDofTileH - 1) / kDofTileH);
         resolve_dof8_kernel<<<g8, 256, 0, s>>>(d_colours, d_focal, c->W, c->H, y0, y1, dst);
         c->launches++;

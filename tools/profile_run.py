@@ -19,6 +19,19 @@ if which == "rt":
     for _ in range(3):
         ctx.rt_frame_device_async(0, H, surf.data_ptr(), col.data_ptr())
     ctx.synchronize()
+elif which == "dof":
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    fp = pkg.default_frame_params(0, W, H)
+    fp.dofEnabled = 1
+    ctx.set_frame(fp)
+    col = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    foc = torch.empty((H, W), dtype=torch.float32, device=dev)
+    surf = torch.empty((H, W), dtype=torch.int32, device=dev)
+    ctx.rt_draw_device_async(0, H, col.data_ptr(), 0, foc.data_ptr())
+    for _ in range(3):
+        ctx.resolve_surface_device_async(0, H, col.data_ptr(), foc.data_ptr(), surf.data_ptr())
+    ctx.synchronize()
 elif which == "ras30":
     ctx = pkg.Context(W, H)
     ctx.set_triangles(tris)
