@@ -93,7 +93,7 @@ SYMBOLS = [
     "b2r_set_triangles", "b2r_set_culled", "b2r_set_frame", "b2r_rt_draw", "b2r_ras_draw", "b2r_ras_cull",
     "b2r_resolve_surface", "b2r_resolve_bgr8", "b2r_bmp_payload_bytes", "b2r_write_bmp", "b2r_rt_frame",
     "b2r_ras_frame", "b2r_set_stream", "b2r_get_stream", "b2r_synchronize", "b2r_rt_draw_device_async",
-    "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_rt_frame_device_async", "b2r_ras_frame_device_async", "b2r_rt_frame_split_device_async", "b2r_launch_count", "b2r_get_stats",
+    "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_rt_frame_device_async", "b2r_ras_frame_device_async", "b2r_rt_frame_split_device_async", "b2r_pin_host_buffer", "b2r_unpin_host_buffer", "b2r_launch_count", "b2r_get_stats",
     "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_scene_cornell_box",
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
     "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
@@ -143,6 +143,8 @@ def load_library():
     lib.b2r_resolve_surface_device_async.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.b2r_rt_frame_device_async.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     lib.b2r_ras_frame_device_async.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    lib.b2r_pin_host_buffer.argtypes = [vp, vp, C.c_size_t]
+    lib.b2r_unpin_host_buffer.argtypes = [vp, vp]
     lib.b2r_rt_frame_split_device_async.argtypes = [vp, i32, i32, C.POINTER(vp), i32, vp, vp, vp]
     lib.b2r_shared_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp), vp]
     lib.b2r_shared_free.argtypes = [vp, vp]
@@ -316,6 +318,13 @@ class Context:
         self._chk(self.lib.b2r_ras_draw_device_async(self.handle, y0, y1, C.c_void_p(d_depth),
                                                      C.c_void_p(d_colours), C.c_void_p(d_focal),
                                                      C.c_void_p(d_winner)))
+
+    def pin_host_buffer(self, array):
+        """Page-lock a numpy array that will receive frames (cudaHostRegister)."""
+        self._chk(self.lib.b2r_pin_host_buffer(self.handle, _ptr(array), array.nbytes))
+
+    def unpin_host_buffer(self, array):
+        self._chk(self.lib.b2r_unpin_host_buffer(self.handle, _ptr(array)))
 
     def rt_frame_split_device_async(self, part, nparts, surfaces, d_colours=0, d_closest=0, d_focal=0):
         """Tile rows part, part+nparts, ... of the frame, every pixel stored into all `surfaces` (device addresses)."""

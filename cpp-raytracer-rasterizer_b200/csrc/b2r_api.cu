@@ -776,6 +776,34 @@ int b2r_shared_open(b2r_ctx* ctx, const void* handle, void** d_ptr) {
     return B2R_OK;
 }
 
+// Page-lock a caller-owned host buffer (e.g. screen->pixels, pixelColours) so the copies of the frame calls run at
+// full PCIe speed and overlap the kernels; pageable memory goes through the driver's staging buffer instead.
+int b2r_pin_host_buffer(b2r_ctx* ctx, void* host, size_t bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!host || bytes == 0) return fail(c, B2R_E_INVALID, "pin_host_buffer: null buffer");
+    cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return B2R_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaHostRegister");
+    return B2R_OK;
+}
+
+int b2r_unpin_host_buffer(b2r_ctx* ctx, void* host) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!host) return B2R_OK;
+    cudaError_t e = cudaHostUnregister(host);
+    if (e == cudaErrorHostMemoryNotRegistered) {
+        cudaGetLastError();
+        return B2R_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(c, e, "cudaHostUnregister");
+    return B2R_OK;
+}
+
 int b2r_copy_device_async(b2r_ctx* ctx, void* d_dst, const void* d_src, size_t bytes) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;

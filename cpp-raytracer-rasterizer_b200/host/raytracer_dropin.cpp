@@ -62,11 +62,24 @@ int Initialize(int width, int height, int device) {
     LoadTestModel(triangles);                            // :149
     g_uploaded = nullptr;
     isUpdated = true;
-    return g_rc = b2r_create(&g_ctx, device, width, height);
+    g_rc = b2r_create(&g_ctx, device, width, height);
+    if (g_rc == 0) {  // the frame arrays receive every Draw(): page-lock them so the copies overlap the tracing
+        b2r_pin_host_buffer(g_ctx, screenPixels.data(), n * sizeof(uint32_t));
+        b2r_pin_host_buffer(g_ctx, pixelColours.data(), n * sizeof(vec3));
+        b2r_pin_host_buffer(g_ctx, closestIntersections.data(), n * sizeof(Intersection));
+        b2r_pin_host_buffer(g_ctx, focalDistances.data(), n * sizeof(float));
+    }
+    return g_rc;
 }
 
 void Shutdown() {
-    if (g_ctx) b2r_destroy(g_ctx);
+    if (g_ctx) {
+        b2r_unpin_host_buffer(g_ctx, screenPixels.data());
+        b2r_unpin_host_buffer(g_ctx, pixelColours.data());
+        b2r_unpin_host_buffer(g_ctx, closestIntersections.data());
+        b2r_unpin_host_buffer(g_ctx, focalDistances.data());
+        b2r_destroy(g_ctx);
+    }
     g_ctx = nullptr;
 }
 

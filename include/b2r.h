@@ -149,6 +149,12 @@ int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* pixelColours,
 int b2r_ras_frame(b2r_ctx* ctx, uint32_t* surface, float* depthBuffer, float* pixelColours,
                   float* focalDistances, int32_t* winnerIndex);
 
+/* Optional: page-lock a caller-owned output buffer (screen->pixels, pixelColours, ...) once, so that the copies
+ * of b2r_rt_frame / b2r_ras_frame / b2r_*_draw run at full PCIe speed and overlap the kernels.  Without it the
+ * calls work the same, only slower (pageable memory is copied through the driver's staging buffer).  Idempotent. */
+int b2r_pin_host_buffer(b2r_ctx* ctx, void* host, size_t bytes);
+int b2r_unpin_host_buffer(b2r_ctx* ctx, void* host);
+
 /* ---- device-resident entry points (no host copies) ---------------------- */
 /* For callers that keep frames in HBM (multi-GPU band gathers, benchmarks).
  * All pointers are DEVICE pointers on the context's GPU, full-frame arrays as

@@ -192,3 +192,24 @@ def test_stl_mesh_end_to_end(pkg, oracle, tmp_path):
     ctx.set_frame(fr)
     rt_equal(ctx.rt_draw(), oracle.rt_draw(tris, fr, w, h))
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_pinned_host_buffers(pkg):
+    """b2r_pin_host_buffer: frames land in a page-locked caller buffer exactly as in a pageable one; pinning twice
+    and unpinning something that was never pinned are not errors."""
+    w, h = 320, 264
+    ctx = pkg.Context(w, h)
+    ctx.set_triangles(pkg.cornell_box())
+    ctx.set_frame(pkg.default_frame_params(0, w, h))
+    want = ctx.rt_frame()
+    buf = np.zeros((h, w), np.uint32)
+    ctx.pin_host_buffer(buf)
+    ctx.pin_host_buffer(buf)
+    for _ in range(2):
+        buf[:] = 0xDEADBEEF
+        ctx.rt_frame(buf)
+        assert np.array_equal(buf, want)
+    ctx.unpin_host_buffer(buf)
+    ctx.unpin_host_buffer(np.zeros(16, np.uint32))
+    ctx.close()
