@@ -342,6 +342,25 @@ def run_gpu_arm(args, pkg):
         extra["band_split_fused"] = {"ms_per_frame": fms, "value": rays / (fms * 1e-3) / 1e6, "unit": "Mrays/s",
                                      "scaling": "strong",
                                      "exchange": "trace kernel stores into peer-mapped surfaces (CUDA IPC over NVLink), tile rows interleaved across ranks"}
+        # rasteriser config 4, sort-first: the 1,004,670 triangles are replicated, every rank rasterises and shades
+        # its row band and the shade kernel's surface rows are gathered with NCCL.  Per-triangle work (vertex
+        # shading, classification) is not divided by the band, so this split is bounded by it.
+        rctx = pkg.Context(W4K, H4K, device=local)
+        rctx.set_stream(stream.cuda_stream)
+        rctx.set_triangles(pkg.tessellate(tris, 183))
+        rctx.set_frame(pkg.default_frame_params(1, W4K, H4K))
+        rctx.ras_cull()
+        def ras_band():
+            rctx.ras_frame_device_async(y0, y1, d_surf.data_ptr())
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(d_surf.view(-1), d_surf.view(-1)[y0 * W4K:y1 * W4K])
+        rms = timed_loop(ras_band, max(args.steps // 4, 5), args.warmup)
+        t = torch.tensor([rms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rms = float(t.item()) / max(args.steps // 4, 5)
+        extra["ras_band_split_4k_1m_tris"] = {"ms_per_frame": rms, "frames_per_s": 1e3 / rms, "scaling": "strong",
+                                              "collective": "nccl all_gather of 32-bit surface bands"}
+        rctx.close()
         barrier()
         for r in range(world):
             if r != rank:

@@ -2,8 +2,9 @@
 
 Single-frame split: every rank renders its row band of the same frame, resolves it with ONE kernel straight
 into every rank's surface (peer-mapped buffers, stores over NVLink), barrier, and every rank compares the
-assembled frame with a frame it rendered alone.  Also checks the NCCL all-gather variant and the
-frame-partitioned orbit."""
+assembled frame with a frame it rendered alone.  Also checks the one-kernel split (interleaved tile rows, trace
+kernel stores to peers), the NCCL all-gather variant, the frame-partitioned orbit and the rasteriser's sort-first
+row-band split."""
 import os
 import sys
 
@@ -99,6 +100,34 @@ def main():
             ctx.synchronize()
             alone.append(int(surf.to(torch.int64).sum()))
         assert alone == sums.tolist(), (alone, sums.tolist())
+    # --- rasteriser, sort-first: triangle list replicated, every rank rasterises and shades its row band only;
+    # exchange by peer stores of the resolve kernel and, separately, by the NCCL band gather
+    rctx = pkg.Context(w, h, device=local)
+    rctx.set_stream(stream.cuda_stream)
+    rtris = pkg.tessellate(pkg.cornell_box(), 6)  # 1,080 triangles
+    rctx.set_triangles(rtris)
+    rctx.set_frame(pkg.default_frame_params(1, w, h))
+    rctx.ras_cull()
+    ras_ref = torch.zeros((h, w), dtype=torch.int32, device=dev)
+    rctx.ras_frame_device_async(0, h, ras_ref.data_ptr())
+    rctx.synchronize()
+    dist.barrier()
+    rctx.ras_draw_device_async(y0, y1, 0, col.data_ptr(), 0, 0)
+    rctx.resolve_surface_multi_device_async(y0, y1, col.data_ptr(), 0, ptrs)
+    rctx.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ctx.copy_device_async(tmp.data_ptr(), mine, w * h * 4)
+    ctx.synchronize()
+    assert torch.equal(tmp, ras_ref), f"rank {rank}: rasteriser band split (peer stores) differs from the single-GPU frame"
+    surf.zero_()
+    rctx.ras_frame_device_async(y0, y1, surf.data_ptr())
+    rctx.synchronize()
+    par.gather_bands(surf, rank, world)
+    torch.cuda.synchronize(dev)
+    assert torch.equal(surf, ras_ref), f"rank {rank}: rasteriser band split (NCCL gather) differs"
+    rctx.close()
+
     dist.barrier()
     for r in range(world):
         if r != rank:
