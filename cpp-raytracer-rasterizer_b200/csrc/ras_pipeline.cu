@@ -497,8 +497,14 @@ __device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long
         in.r.rp[0] = q1.z; in.r.rp[1] = q1.w; in.r.rp[2] = 1.0f;
         in.r.pad[0] = in.r.pad[1] = 0;
     }
-    in.normal = mk3(t[9], t[10], t[11]);
-    in.color = mk3(t[12], t[13], t[14]);
+    if (a.stride == 64) {  // the rasteriser's own 64-byte Triangle: records are 16-byte aligned, two 128-bit loads
+        const float4 n4 = reinterpret_cast<const float4*>(t)[2], c4 = reinterpret_cast<const float4*>(t)[3];
+        in.normal = mk3(n4.y, n4.z, n4.w);
+        in.color = mk3(c4.x, c4.y, c4.z);
+    } else {
+        in.normal = mk3(t[9], t[10], t[11]);
+        in.color = mk3(t[12], t[13], t[14]);
+    }
     return in;
 }
 
