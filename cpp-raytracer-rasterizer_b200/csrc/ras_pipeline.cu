@@ -69,7 +69,7 @@ constexpr int kCoordLimit = 1 << 24;
 
 // ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
 constexpr int kSmallRows = 20;      // triangles up to this many polygon rows are finished by ras_small
-constexpr int kWindowRows = 8;      // rows whose ends are held in shared memory at a time (one walk per window)
+constexpr int kWindowRows = 7;      // rows whose ends are held in shared memory at a time (one walk per window)
 constexpr int kSmallThreads = 128;
 
 struct RasCounters {
@@ -124,7 +124,7 @@ __device__ __forceinline__ EdgeStep edge_begin(const RPixel& a, const RPixel& b)
     return e;
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 7) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
+__global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
                                                                    TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
                                                                    int2* __restrict__ triInfo, SmallRow* __restrict__ rowRec,
                                                                    RasCounters* __restrict__ ctr) {
