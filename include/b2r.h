@@ -160,7 +160,9 @@ int b2r_unpin_host_buffer(b2r_ctx* ctx, void* host);
  * All pointers are DEVICE pointers on the context's GPU, full-frame arrays as
  * above, may be NULL.  Work is enqueued on the context's stream;
  * b2r_synchronize() waits for it.  cuda_stream (a cudaStream_t cast to void*)
- * replaces the context's own stream when non-NULL at b2r_set_stream(). */
+ * replaces the context's own stream when non-NULL at b2r_set_stream().  A context is driven by one host thread
+ * and its draws are ordered on that one stream (they share scheduler words and scratch buffers); use one context
+ * per stream for concurrent frames. */
 int b2r_set_stream(b2r_ctx* ctx, void* cuda_stream);
 void* b2r_get_stream(b2r_ctx* ctx);
 int b2r_synchronize(b2r_ctx* ctx);
