@@ -111,7 +111,7 @@ void LoadTestModel(std::vector<Triangle>& out) {
     const int n = b2r_scene_cornell_box(raw, 30, 64);
     for (int i = 0; i < n; ++i) {
         Triangle t(vec3(0, 0, 0), vec3(0, 0, 0), vec3(0, 0, 0), vec3(0, 0, 0));
-        std::memcpy(&t, raw + 64 * i, 60);
+        std::memcpy(static_cast<void*>(&t), raw + 64 * i, 60);  // v0, v1, v2, normal, color: 15 floats
         t.isCulled = false;
         out.push_back(t);
     }
