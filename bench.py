@@ -95,7 +95,11 @@ def run_reference_arm(args, pkg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_reference_sample(pkg, row_step=34, steps=args.steps, warmup=args.warmup)
+    # Every 4th row of the frame (0.6 s per step on 16 threads) as long as the run stays near two minutes; a thinner
+    # sample would leave the reference's OpenMP threads unevenly loaded and understate it.
+    budget_steps = max(1, args.steps + args.warmup)
+    row_step = max(4, -(-4 * budget_steps * 6 // 1200))  # ceil(4 * steps * 0.6 s / 120 s)
+    base = cpu_reference_sample(pkg, row_step=row_step, steps=args.steps, warmup=args.warmup)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
