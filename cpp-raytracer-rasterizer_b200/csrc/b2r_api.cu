@@ -87,6 +87,19 @@ int check_band(Ctx* c, int y0, int y1) {
     return B2R_OK;
 }
 
+const char* const kRasCapacityText =
+    "rasteriser: a projected triangle exceeds 2^22 rows or 2^24 pixels in a coordinate "
+    "(a vertex at or behind the camera plane); the reference cannot draw it either";
+
+// Rasteriser draws of small scenes are plain launch sequences without a readback; their capacity flag is looked at
+// when the caller synchronises (host-buffer calls do so themselves, asynchronous callers through b2r_synchronize).
+int ras_deferred_error(Ctx* c) {
+    const cudaError_t e = ras_take_error(c);
+    if (e == cudaErrorInvalidValue) return fail(c, B2R_E_CAPACITY, kRasCapacityText);
+    if (e != cudaSuccess) return cuda_fail(c, e, "rasteriser error flag");
+    return B2R_OK;
+}
+
 // D2H of rows [y0,y1) of a full-frame array with `bpp` bytes per pixel.
 int copy_rows_out(Ctx* c, void* host, const void* dev, int y0, int y1, size_t bpp) {
     if (!host || y1 <= y0) return B2R_OK;
@@ -186,7 +199,7 @@ int b2r_synchronize(b2r_ctx* ctx) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
     CU(cudaStreamSynchronize(c->stream), "cudaStreamSynchronize");
-    return B2R_OK;
+    return ras_deferred_error(c);
 }
 
 int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride) {
@@ -631,9 +644,7 @@ static int ras_launch_band(Ctx* c, int y0, int y1, float* d_dep, float* d_col, f
     a.surface = d_surf;
     a.stats = c->statsOn ? c->stats.as<unsigned long long>() : nullptr;
     cudaError_t e = launch_ras_draw(c, a, c->stream);
-    if (e == cudaErrorInvalidValue)
-        return fail(c, B2R_E_CAPACITY, "rasteriser: a projected triangle exceeds 2^22 rows or 2^24 pixels in a coordinate "
-                                      "(a vertex at or behind the camera plane); the reference cannot draw it either");
+    if (e == cudaErrorInvalidValue) return fail(c, B2R_E_CAPACITY, kRasCapacityText);
     if (e != cudaSuccess) return cuda_fail(c, e, "rasteriser kernels");
     return B2R_OK;
 }
@@ -687,6 +698,7 @@ static int ras_draw_host(Ctx* c, int y0, int y1, float* dep, float* col, float* 
     if (int rc = copy_rows_out(c, foc, c->focal.p, y0, y1, 4)) return rc;
     if (int rc = copy_rows_out(c, win, c->winner.p, y0, y1, 4)) return rc;
     CU(cudaStreamSynchronize(c->stream), "rasteriser draw");
+    if (int rc = ras_deferred_error(c)) return rc;
     c->coloursValid = needCol;
     c->surfaceValid = surface && y0 == 0 && y1 == c->H;
     return B2R_OK;

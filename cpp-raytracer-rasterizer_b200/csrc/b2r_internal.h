@@ -111,6 +111,7 @@ struct RasLaunch {
     int32_t* winner;
     uint32_t* surface;         // may be null: the resolved XRGB surface (only without depth of field)
     unsigned long long* stats;
+    int bandSlots;             // large-triangle path with fixed-capacity slots (set by launch_ras_draw)
 };
 
 struct Ctx;
@@ -121,6 +122,9 @@ cudaError_t launch_tri_prep(Ctx* c, cudaStream_t s);
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s);
 cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s);
 cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s);
+// After the stream has been synchronised: cudaErrorInvalidValue if a draw since the last call hit the row/coordinate
+// limits (-> B2R_E_CAPACITY), cudaSuccess otherwise.
+cudaError_t ras_take_error(Ctx* c);
 cudaError_t launch_resolve_surface(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
                                    uint32_t* d_surface, cudaStream_t s);
 cudaError_t launch_resolve_surface_multi(Ctx* c, int y0, int y1, const float* d_colours, const float* d_focal,
@@ -204,6 +208,7 @@ struct Ctx {
     unsigned long long launches = 0;
     int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0, optDofVariant = 0;
     int lastDraw = -1;  // 0 raytracer, 1 rasteriser
+    bool rasErrPending = false;  // an asynchronous rasteriser draw left its capacity flag to be checked (see ras_take_error)
     // what the context's own buffers hold after the last host-buffer draw: the fused raytracer frame may leave only
     // the resolved surface (no pixelColours); b2r_resolve_* then start from it
     bool coloursValid = false, surfaceValid = false;

@@ -74,7 +74,8 @@ constexpr int kSmallThreads = 128;
 
 struct RasCounters {
     unsigned nBig, bigRows, bigSamples, err;
-    unsigned long long pad;
+    unsigned sticky;  // like err, but only cleared by the host after it has been reported (asynchronous draws)
+    unsigned pad;
 };
 
 // Row ends of one polygon row of a small triangle, written by ras_small for the shade pass: 32 bytes at the
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
         const int rows = maxY - minY + 1;  // :682
         if (bad || rows > kMaxRowsPerTriangle) {
             atomicExch(&ctr->err, 1u);  // the reference would try to allocate/walk an absurd row count
+            atomicExch(&ctr->sticky, 1u);
         } else if (rows > kSmallRows) {
             const unsigned samples = (unsigned)(abs(v[0].y - v[1].y) + abs(v[1].y - v[2].y) + abs(v[2].y - v[0].y) + 3);
             const unsigned slot = atomicAdd(&ctr->nBig, 1u);
@@ -177,9 +179,19 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
             s.rowBase = s.sampleBase = 0;
             s.drawn = 1;
             s.tri = i;
-            bigTs[slot] = s;
-            bigCounts[slot] = make_uint2((unsigned)rows, samples);
-            triInfo[i] = make_int2((int)slot, minY);
+            if (a.bandSlots) {
+                // fixed-capacity slots: only rows of the band are kept, so a triangle needs at most bandH row
+                // records and bandH samples per edge; rows are addressed by y - y0 (no scan, no readback)
+                const unsigned bandH = (unsigned)(a.y1 - a.y0);
+                s.rowBase = slot * bandH;
+                s.sampleBase = slot * 3u * bandH;
+                bigTs[slot] = s;
+                triInfo[i] = make_int2((int)slot, a.y0);
+            } else {
+                bigTs[slot] = s;
+                bigCounts[slot] = make_uint2((unsigned)rows, samples);
+                triInfo[i] = make_int2((int)slot, minY);
+            }
             nDrawn = 1;
             nRows = (unsigned long long)rows;
         } else {
@@ -335,19 +347,24 @@ __global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __r
 // One thread per (triangle, edge, chain): the five accumulation chains of an edge (x, zinv, pos3d.xyz) are
 // independent of each other, so each runs its own serial loop -- 15 threads per triangle instead of 3 -- and writes
 // its field of every sample.  A 2160-row edge is latency-bound: one dependent FADD per step and thread.
-__global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* listed large triangles */, EdgeSample* __restrict__ samples,
-                                 unsigned* __restrict__ rowOwner) {
+// BAND: fixed-capacity slots (see ras_small): the number of listed triangles is read from the device counter, the walk
+// still runs over every step (the accumulation is serial) but only samples on rows of the band are stored, at y - y0.
+template <bool BAND>
+__global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* listed large triangles (upper bound if BAND) */,
+                                 const RasCounters* __restrict__ ctr, EdgeSample* __restrict__ samples,
+                                 unsigned* __restrict__ rowOwner, int y0, int y1) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = gid / 15, rem = gid - 15 * i, e = rem / 5, ch = rem - 5 * e;
-    if (i >= T) return;
+    if (i >= (BAND ? (int)ctr->nBig : T)) return;
     const TriSetup s = ts[i];
     if (!s.drawn) return;
-    if (rem < 5)  // five threads share the owner table of this triangle's rows
+    if (!BAND && rem < 5)  // five threads share the owner table of this triangle's rows
         for (int r = rem; r < s.rows; r += 5) rowOwner[s.rowBase + r] = (unsigned)i;
     const int j = (e + 1) % 3;  // :707
     const int n = abs(s.vy[e] - s.vy[j]) + 1;  // :712
     unsigned off = s.sampleBase;
-    for (int k = 0; k < e; ++k) off += (unsigned)(abs(s.vy[k] - s.vy[(k + 1) % 3]) + 1);
+    if (BAND) off += (unsigned)e * (unsigned)(y1 - y0);
+    else for (int k = 0; k < e; ++k) off += (unsigned)(abs(s.vy[k] - s.vy[(k + 1) % 3]) + 1);
     const float div = (float)max(n - 1, 1);  // :622
     // Pixel operator- (TestModel.h:82-85) then fPixel operator/ (:124-127); fPixel(Pixel&) for the start value
     float cur, step;
@@ -362,7 +379,39 @@ __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* liste
         step = xdiv_step(xsub(s.vp[3 * j + (ch - 2)], cur), div);
     }
     float* out = reinterpret_cast<float*>(samples + off) + ch;  // field ch of sample 0; samples are 5 words apart
-    if (ch == 0) {
+    if (BAND) {
+        // step k lies on row vy[e] + sgn*k: the steps before the band only accumulate, the steps inside it are
+        // stored, the steps after it are not needed by anyone
+        const int ya = s.vy[e], sgn = (s.vy[j] > ya) - (s.vy[j] < ya);
+        int kLo, kHi;
+        if (sgn > 0) {
+            kLo = y0 - ya;
+            kHi = y1 - 1 - ya;
+        } else if (sgn < 0) {
+            kLo = ya - (y1 - 1);
+            kHi = ya - y0;
+        } else {
+            kLo = (ya >= y0 && ya < y1) ? 0 : 1;
+            kHi = 0;
+        }
+        kLo = max(kLo, 0);
+        kHi = min(kHi, n - 1);
+        if (kLo > kHi) return;
+        for (int k = 0; k < kLo; ++k) cur = xadd(cur, step);  // :626-636 -- serial float accumulation, order matters
+        out += 5 * (ya + sgn * kLo - y0);
+        const int stride = 5 * sgn;
+        if (ch == 0) {
+            for (int k = kLo; k <= kHi; ++k, out += stride) {
+                *reinterpret_cast<int*>(out) = f2i_x86(cur);
+                cur = xadd(cur, step);
+            }
+        } else {
+            for (int k = kLo; k <= kHi; ++k, out += stride) {
+                *out = cur;
+                cur = xadd(cur, step);
+            }
+        }
+    } else if (ch == 0) {
         for (int k = 0; k < n; ++k, out += 5) {  // :626-636 -- serial float accumulation, order matters
             *reinterpret_cast<int*>(out) = f2i_x86(cur);
             cur = xadd(cur, step);
@@ -376,7 +425,9 @@ __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* liste
 }
 
 // ---- stage 3: ComputePolygonRows' per-row resolve (:716-733) + DrawRows/DrawLineSDL/Bresenham ----
-__device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSample* __restrict__ samples, int y) {
+// bandH > 0: band-slot layout, edge e's sample of row y sits at sampleBase + e*bandH + (y - y0)
+__device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSample* __restrict__ samples, int y,
+                                              int bandH = 0, int y0 = 0) {
     RowRec r;
     r.lx = INT_MAX;    // :696
     r.rx = -INT_MAX;   // :697
@@ -389,7 +440,8 @@ __device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSampl
         const int ya = s.vy[e], yb = s.vy[j];
         const int n = abs(ya - yb) + 1;
         if (y >= min(ya, yb) && y <= max(ya, yb)) {
-            const EdgeSample q = samples[off + (unsigned)abs(y - ya)];
+            const EdgeSample q = bandH > 0 ? samples[s.sampleBase + (unsigned)(e * bandH + (y - y0))]
+                                           : samples[off + (unsigned)abs(y - ya)];
             if (q.x < r.lx) {  // :718 strict: the first edge to reach an extreme keeps its attributes
                 r.lx = q.x;
                 r.lz = q.zinv;
@@ -419,7 +471,9 @@ __device__ __forceinline__ void raster_span(unsigned long long* __restrict__ key
 constexpr int kShortRow = 8;
 
 
+template <bool BAND>
 __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restrict__ ts,
+                                                       const RasCounters* __restrict__ ctr,
                                                        const EdgeSample* __restrict__ samples,
                                                        const unsigned* __restrict__ rowOwner, unsigned nRows,
                                                        RowRec* __restrict__ rows,
@@ -430,13 +484,17 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
     int lx = 0, pixels = 0, i0 = 0, i1 = 0, y = 0;
     float lz = 0.f, zstep = 0.f;
     unsigned tri = 0;
-    if (rid < nRows) {
-        const TriSetup s = ts[rowOwner[rid]];
+    const int bandH = y1 - y0;
+    // BAND: thread rid <-> (slot rid / bandH, row y0 + rid % bandH); otherwise the rows of the listed triangles are
+    // packed and rowOwner names the triangle
+    const unsigned slot = BAND ? rid / (unsigned)bandH : 0u;
+    if (BAND ? slot < ctr->nBig : rid < nRows) {
+        const TriSetup s = ts[BAND ? slot : rowOwner[rid]];
         tri = (unsigned)s.tri;
-        y = s.minY + (int)(rid - s.rowBase);
+        y = BAND ? y0 + (int)(rid - slot * (unsigned)bandH) : s.minY + (int)(rid - s.rowBase);
         // DrawRows (:743): rows with y outside the screen are skipped; outside the band: another GPU's
-        if (y >= y0 && y < y1) {
-            RowRec r = resolve_row(s, samples, y);
+        if (y >= y0 && y < y1 && y >= s.minY && y < s.minY + s.rows) {
+            RowRec r = BAND ? resolve_row(s, samples, y, bandH, y0) : resolve_row(s, samples, y);
             rows[rid] = r;
             lx = r.lx;
             lz = r.lz;
@@ -640,7 +698,25 @@ cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s) {
 // Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
 
 // Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
-cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
+// Scenes of few triangles (T * band height row slots within this budget: ~100 MB of row records, ~200 MB of edge
+// samples) take the large-triangle path with fixed-capacity slots: nothing is read back, the frame is a plain
+// sequence of launches.  Larger scenes size the buffers from counters read back after the first kernel.
+constexpr size_t kBandSlotLimit = 2u << 20;
+
+cudaError_t ras_take_error(Ctx* c) {
+    if (!c->rasErrPending) return cudaSuccess;
+    c->rasErrPending = false;
+    RasCounters* ctr = c->rasScratch.as<RasCounters>();
+    unsigned flag = 0;
+    cudaError_t e = cudaMemcpy(&flag, &ctr->sticky, sizeof flag, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return e;
+    if (!flag) return cudaSuccess;
+    e = cudaMemset(&ctr->sticky, 0, sizeof flag);
+    return e != cudaSuccess ? e : cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
+    RasLaunch a = a0;
     const int T = a.T;
     const int bandH = a.y1 - a.y0;
     cudaError_t e;
@@ -649,7 +725,11 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     const size_t offCtr = 0, offCounts = 256, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
                  offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
                  offTotals = align_up(offSums + sizeof(uint2) * (size_t)nbMax, 256), scratchBytes = offTotals + 256;
+    const void* scratchBefore = c->rasScratch.p;
     if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
+    if (c->rasScratch.p != scratchBefore &&  // fresh memory: the sticky error flag starts clear
+        (e = cudaMemsetAsync(c->rasScratch.p, 0, 256, s)) != cudaSuccess)
+        return e;
     if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int2) * (size_t)(T + 1) + 1024)) != cudaSuccess) return e;
     if ((e = c->rasSmall.reserve(sizeof(SmallRow) * (size_t)kSmallRows * (size_t)(T + 1))) != cudaSuccess) return e;
     if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
@@ -664,7 +744,10 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
     TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int2) * (size_t)(T + 1), 256));
     unsigned long long* keys = c->rasKeys.as<unsigned long long>();
 
-    if ((e = cudaMemsetAsync(ctr, 0, sizeof(RasCounters), s)) != cudaSuccess) return e;
+    const bool bandSlots = T > 0 && (size_t)T * (size_t)bandH <= kBandSlotLimit && c->optRasVariant != 1;
+    a.bandSlots = bandSlots ? 1 : 0;
+    // the sticky flag (second half of the struct) survives until the host has reported it
+    if ((e = cudaMemsetAsync(ctr, 0, offsetof(RasCounters, sticky), s)) != cudaSuccess) return e;
     // depthBuffer = 0 (:188): the shade pass of the previous frame leaves the key buffer cleared; clear it here
     // only when the buffer is new or was last used for a different band size
     const size_t keyBytes = sizeof(unsigned long long) * (size_t)bandH * a.W;
@@ -681,14 +764,35 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
             if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
             attrSet = true;
         }
+        if (bandSlots) {  // worst case: every triangle is large
+            const size_t nSlots = (size_t)T * (size_t)bandH;
+            if ((e = c->rasRows.reserve(sizeof(RowRec) * nSlots + sizeof(EdgeSample) * 3 * nSlots + 1024)) != cudaSuccess) return e;
+        }
         ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, triInfo, rowRec, ctr);
         c->launches++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (bandSlots) {
+        const size_t nSlots = (size_t)T * (size_t)bandH;
+        unsigned char* rb = c->rasRows.as<unsigned char>();
+        RowRec* rows = reinterpret_cast<RowRec*>(rb);
+        EdgeSample* samples = reinterpret_cast<EdgeSample*>(rb + align_up(sizeof(RowRec) * nSlots, 256));
+        rowsPtr = rows;
+        ras_edges_kernel<true><<<(15 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, nullptr, a.y0, a.y1);
+        ras_rows_kernel<true><<<(unsigned)((nSlots + 255) / 256), 256, 0, s>>>(ts, ctr, samples, nullptr, 0u, rows, keys, a.W, a.y0,
+                                                                              a.y1, a.stats);
+        c->launches += 2;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        c->rasErrPending = true;  // checked by the caller's next synchronising call (ras_take_error)
+    } else if (T > 0) {
         // how many large triangles / rows / edge samples: 16 bytes back to size the big path
         if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
         host = *reinterpret_cast<RasCounters*>(c->pinned);
-        if (host.err) return cudaErrorInvalidValue;
+        if (host.err) {
+            cudaMemsetAsync(&ctr->sticky, 0, sizeof(unsigned), s);  // reported right here
+            return cudaErrorInvalidValue;
+        }
     }
     if (host.nBig > 0) {
         const int nBig = (int)host.nBig;
@@ -706,8 +810,8 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
         scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, nBig);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
         scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
-        ras_edges_kernel<<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, samples, owner);
-        ras_rows_kernel<<<(nRows + 255) / 256, 256, 0, s>>>(ts, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
+        ras_edges_kernel<false><<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, ctr, samples, owner, a.y0, a.y1);
+        ras_rows_kernel<false><<<(nRows + 255) / 256, 256, 0, s>>>(ts, ctr, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
         c->launches += 5;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -20,8 +20,15 @@ def check(got, want):
     assert np.array_equal(bits(got["focalDistances"]), bits(want["focalDistances"]))
 
 
-def draw_both(pkg, oracle, tris, fp, w, h, cull=True):
+@pytest.fixture(params=[0, 1], ids=["slots", "readback"])
+def ras_variant(request):
+    """Large-triangle path: 0 = fixed-capacity slots without readback (small scenes), 1 = counters read back."""
+    return request.param
+
+
+def draw_both(pkg, oracle, tris, fp, w, h, cull=True, variant=0):
     ctx = pkg.Context(w, h)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, variant)
     ctx.enable_stats(True)
     ctx.set_triangles(tris)
     ctx.set_frame(fp)
@@ -40,12 +47,12 @@ def draw_both(pkg, oracle, tris, fp, w, h, cull=True):
     return got, want, culled
 
 
-def test_config2_cornell_500(pkg, oracle):
+def test_config2_cornell_500(pkg, oracle, ras_variant):
     """BASELINE config 2: Cornell box 500x500, per-pixel illumination, 1/z depth buffer."""
     w = h = 500
     tris = pkg.cornell_box()
     fp = pkg.default_frame_params(1, w, h)
-    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h)
+    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h, variant=ras_variant)
     check(got, want)
     # known answers of the reference itself (SURVEY.md section 7 step 1)
     assert "".join(map(str, culled)) == "000000000000001111000011110011"
@@ -54,15 +61,15 @@ def test_config2_cornell_500(pkg, oracle):
 
 
 @pytest.mark.parametrize("w,h", [(96, 64), (64, 96), (160, 120), (33, 17)])
-def test_small_screens(pkg, oracle, w, h):
+def test_small_screens(pkg, oracle, w, h, ras_variant):
     tris = pkg.cornell_box()
     fp = pkg.default_frame_params(1, w, h)
-    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, variant=ras_variant)
     check(got, want)
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
-def test_random_scenes(pkg, oracle, seed):
+def test_random_scenes(pkg, oracle, seed, ras_variant):
     """Random soups in front of a rotated camera: off-screen spans, exact-zinv ties, several lights, no culling."""
     rng = np.random.default_rng(seed)
     w, h = 128, 96
@@ -75,7 +82,7 @@ def test_random_scenes(pkg, oracle, seed):
     fp.set_camera([0.1, -0.05, -3.0], rot_y(rng.uniform(-0.2, 0.2), 1.01), float(h))
     lights = np.concatenate([rng.uniform(-1, 1, (2, 3)), rng.uniform(0.2, 1, (2, 3)), rng.uniform(2, 20, (2, 1))], 1)
     fp.set_lights(lights.astype(np.float32))
-    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, cull=(seed % 2 == 0))
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, cull=(seed % 2 == 0), variant=ras_variant)
     check(got, want)
     if seed == 4:
         assert (got["winner"] < 30).all()
@@ -135,14 +142,29 @@ def test_empty_and_all_culled(pkg, oracle):
     ctx.close()
 
 
-def test_vertex_behind_camera_is_refused(pkg):
-    """A vertex on the camera plane projects to +-inf: the reference would walk ~2^31 rows; we return an error."""
+def test_vertex_behind_camera_is_refused(pkg, ras_variant):
+    """A vertex on the camera plane projects to +-inf: the reference would walk ~2^31 rows; we return an error --
+    from the host-buffer call itself, and for asynchronous draws of small scenes (no readback) from b2r_synchronize;
+    a good frame afterwards is not affected."""
+    import torch
     w, h = 64, 48
-    tris = pkg.cornell_box()[:1].copy()
+    good = pkg.cornell_box()
+    tris = good[:1].copy()
     tris[0, 2] = -3.0  # v0.z == cameraPos.z
     ctx = pkg.Context(w, h)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, ras_variant)
     ctx.set_triangles(tris)
     ctx.set_frame(pkg.default_frame_params(1, w, h))
     with pytest.raises(pkg.B2RError):
         ctx.ras_draw()
+    col = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+    with pytest.raises(pkg.B2RError):
+        ctx.ras_draw_device_async(0, h, 0, col.data_ptr())
+        ctx.synchronize()
+    ctx.synchronize()  # reported once
+    ctx.set_triangles(good)
+    ctx.ras_cull()
+    ctx.ras_draw()
+    ctx.ras_draw_device_async(0, h, 0, col.data_ptr())
+    ctx.synchronize()
     ctx.close()
