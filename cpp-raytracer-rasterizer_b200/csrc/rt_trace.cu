@@ -809,7 +809,8 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const DevFrame& f = c->hostFrame;
     RtLaunch a = a0;
-    const bool cache = rt_cache_bytes(a.T, f.nOrigins) > 0 && c->optRtVariant != 3;
+    // (one sample per tile: nothing to reuse, the cache would only be rebuilt and stored every time)
+    const bool cache = rt_cache_bytes(a.T, f.nOrigins) > 0 && c->optRtVariant != 3 && f.aaN > 1;
     a.shadowCache = cache ? 1 : 0;
     const size_t smemRes = rt_smem_bytes(a.T, f.nOrigins, f.nLights, true, cache);
     const bool resident = smemRes <= 96 * 1024 && c->optRtVariant != 2;
