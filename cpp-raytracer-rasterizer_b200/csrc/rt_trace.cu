@@ -572,6 +572,8 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
                         const float4 pw = sPow[0];
                         P = mk3(pw.x, pw.y, pw.z);
                     }
+                    bool haveBox = false;  // posLo/posHi: box of the lit lanes' hit points, reduced on first use
+                    V3 posLo = mk3(0.f, 0.f, 0.f), posHi = mk3(0.f, 0.f, 0.f);
                     for (int o = 1; o < nO; ++o, xs += oStrideX, Fo += oStrideF, hdr += cacheQuads) {
                         {
                             const float4 og = ONE ? make_float4(a.fr.light0[0], a.fr.light0[1], a.fr.light0[2], 0.f) : sOrg[o];
@@ -635,9 +637,18 @@ __global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(c
                                     }
                                 }
                                 if (!cached) {
-                                    const float big = 3.0e38f;
-                                    V3 qlo = mk3(warp_min(any ? dv.x : big), warp_min(any ? dv.y : big), warp_min(any ? dv.z : big));
-                                    V3 qhi = mk3(warp_max(any ? dv.x : -big), warp_max(any ? dv.y : -big), warp_max(any ? dv.z : -big));
+                                    // Box of the light->hit vectors dv = lpos - pos of the lit lanes.  The hit points
+                                    // are the same for every light sample of this sub-sample, so their box is
+                                    // reduced once (6 REDUX) and each origin derives its own: subtraction is
+                                    // monotonic, also after rounding, so lpos - posHi <= dv <= lpos - posLo holds for
+                                    // the rounded values the lanes use.
+                                    if (!haveBox) {
+                                        const float big = 3.0e38f;
+                                        posLo = mk3(warp_min(any ? ps.pos.x : big), warp_min(any ? ps.pos.y : big), warp_min(any ? ps.pos.z : big));
+                                        posHi = mk3(warp_max(any ? ps.pos.x : -big), warp_max(any ? ps.pos.y : -big), warp_max(any ? ps.pos.z : -big));
+                                        haveBox = true;
+                                    }
+                                    V3 qlo = xsub3(lpos, posHi), qhi = xsub3(lpos, posLo);
                                     if (cacheQuads) {
                                         const float4 c0 = hdr[0], c1 = hdr[1];
                                         const float px = fmaf(0.25f, qhi.x - qlo.x, 9.765625e-4f * fmaxf(fabsf(qlo.x), fabsf(qhi.x)));
