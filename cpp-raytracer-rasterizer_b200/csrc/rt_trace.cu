@@ -356,7 +356,7 @@ constexpr int kSingleBlockQuads = 32 * 5;
 // ONE (implies SINGLE): one light, one shadow sample (the reference's defaults); the light loop disappears and the
 // light's position and power come from the kernel parameters.
 template <bool RESIDENT, bool TILECULL, bool FILTER, bool STATS, bool SINGLE, bool ONE>
-__global__ void __launch_bounds__(kThreads, ONE ? 4 : 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
+__global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kernel(const __grid_constant__ RtLaunch a) {
     static_assert(RESIDENT || !SINGLE, "SINGLE needs the shared-memory tables");
     static_assert(SINGLE || !ONE, "ONE is a specialisation of SINGLE");
     extern __shared__ __align__(16) unsigned char smem_raw[];
