@@ -26,3 +26,11 @@ for (w, h, k, aa) in [(500, 500, 17, 0), (1920, 1080, 17, 0), (3840, 2160, 17, 0
     rays = st["primary_rays"] + st["shadow_rays"]
     print(f"rt {w}x{h} tris={len(tris)} aa={aa}: {ms:.3f} ms, {rays/ms/1e3:.0f} Mrays/s, exact tests/ray {st['exact_tests']/rays:.2f}")
     ctx.close()
+for (w, h, k) in [(500, 500, 17), (3840, 2160, 17), (3840, 2160, 60)]:
+    tris = pkg.tessellate(pkg.cornell_box(), k)
+    ctx = pkg.Context(w, h); ctx.set_stream(stream.cuda_stream); ctx.set_triangles(tris)
+    ctx.set_frame(pkg.default_frame_params(1, w, h)); ctx.ras_cull()
+    surf = torch.empty((h, w), dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ctx.ras_frame_device_async(0, h, surf.data_ptr()), n=20)
+    print(f"ras {w}x{h} tris={len(tris)}: {ms:.3f} ms")
+    ctx.close()
