@@ -208,6 +208,7 @@ struct Ctx {
     unsigned long long launches = 0;
     int optRtFilter = 1, optRtVariant = 0, optRasVariant = 0, optDofVariant = 0;
     int lastDraw = -1;  // 0 raytracer, 1 rasteriser
+    bool rasCtrDirty = true;     // the rasteriser's per-frame counters need a clear before the next draw
     bool rasErrPending = false;  // an asynchronous rasteriser draw left its capacity flag to be checked (see ras_take_error)
     // what the context's own buffers hold after the last host-buffer draw: the fused raytracer frame may leave only
     // the resolved surface (no pixelColours); b2r_resolve_* then start from it

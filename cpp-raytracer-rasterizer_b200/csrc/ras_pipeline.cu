@@ -602,7 +602,10 @@ __global__ void __launch_bounds__(256, 5) ras_shade_kernel(RasLaunch a, const Tr
                                                         const int2* __restrict__ triInfo,
                                                         const SmallRow* __restrict__ rowRec,
                                                         const RowRec* __restrict__ rows,
-                                                        unsigned long long* __restrict__ keys) {
+                                                        unsigned long long* __restrict__ keys,
+                                                        RasCounters* __restrict__ ctr) {
+    // last kernel of the frame: leave the per-frame counters clear for the next one (no memset in steady state)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctr->nBig = ctr->bigRows = ctr->bigSamples = ctr->err = 0u;
     const int y = a.y0 + blockIdx.y;
     const int xbase = blockIdx.x * (256 * kShadePixels) + threadIdx.x;
     unsigned long long key[kShadePixels];
@@ -759,7 +762,10 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     const bool bandSlots = T > 0 && (size_t)T * (size_t)bandH <= kBandSlotLimit && c->optRasVariant != 1;
     a.bandSlots = bandSlots ? 1 : 0;
     // the sticky flag (second half of the struct) survives until the host has reported it
-    if ((e = cudaMemsetAsync(ctr, 0, offsetof(RasCounters, sticky), s)) != cudaSuccess) return e;
+    // ... and so do the per-frame counters, cleared by the previous frame's shade kernel; clear them here only
+    // after a draw that did not get that far (or on a fresh buffer, above)
+    if (c->rasCtrDirty && (e = cudaMemsetAsync(ctr, 0, offsetof(RasCounters, sticky), s)) != cudaSuccess) return e;
+    c->rasCtrDirty = true;
     // depthBuffer = 0 (:188): the shade pass of the previous frame leaves the key buffer cleared; clear it here
     // only when the buffer is new or was last used for a different band size
     const size_t keyBytes = sizeof(unsigned long long) * (size_t)bandH * a.W;
@@ -829,11 +835,12 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     }
     {
         dim3 grid((a.W + 256 * kShadePixels - 1) / (256 * kShadePixels), bandH);
-        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, triInfo, rowRec, rowsPtr, keys);
+        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, triInfo, rowRec, rowsPtr, keys, ctr);
         c->launches++;
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) {
+        c->rasCtrDirty = false;
         c->rasKeysClean = keyBytes;
         c->rasKeysCleanPtr = keys;
     }
