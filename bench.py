@@ -457,6 +457,23 @@ def other_configs(pkg, torch, dev, stream, flush, local, cpu=False):
     ms = avg_ms(f2)
     out["ras_500x500"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms}
     ctx.close()
+    # config 3, second reading (SURVEY 8d "3b"): 16 jittered light samples per pixel (soft shadows), 1 primary ray
+    ctx = pkg.Context(W4K, H4K, device=local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_triangles(tris)
+    fps = pkg.default_frame_params(0, W4K, H4K)
+    fps.softShadowsEnabled, fps.softShadowsSamples = 1, 16
+    fps.set_random_positions(pkg.jitter_table(1, [0, -0.5, -0.7]))
+    ctx.set_frame(fps)
+    surf4 = torch.empty((H4K, W4K), dtype=torch.int32, device=dev)
+    ms = avg_ms(lambda: ctx.rt_frame_device_async(0, H4K, surf4.data_ptr()))
+    ctx.enable_stats(True)
+    ctx.rt_frame_device_async(0, H4K, surf4.data_ptr())
+    st = ctx.stats()
+    ctx.enable_stats(False)
+    out["rt_4k_soft_shadows_16"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms,
+                                    "Mrays_per_s": (st["primary_rays"] + st["shadow_rays"]) / ms / 1e3}
+    ctx.close()
     # config 4: rasteriser 4K, 1,004,670 triangles
     big = pkg.tessellate(tris, 183)
     ctx = pkg.Context(W4K, H4K, device=local)
