@@ -28,7 +28,9 @@ def test_struct_layouts_match_the_header(pkg, tmp_path):
                    "sizeof(b2r_frame_params),sizeof(b2r_light),sizeof(b2r_intersection),offsetof(b2r_frame_params,randomPositions),"
                    "offsetof(b2r_frame_params,aaEnabled),offsetof(b2r_frame_params,currentReflectance));return 0;}\n")
     exe = tmp_path / "sz"
-    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    # the header is plain C: no C++ (or torch) types in any signature
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     FP = pkg.FrameParams
     assert got == [C.sizeof(FP), C.sizeof(pkg.capi.Light), 20, FP.randomPositions.offset, FP.aaEnabled.offset,
