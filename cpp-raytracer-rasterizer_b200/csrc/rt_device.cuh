@@ -39,9 +39,9 @@ __host__ __device__ inline OriginTri origin_constants(V3 v0, V3 e1, V3 e2, V3 n,
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool exact_hit_core(const TriG& t, V3 be2, V3 e1b, float nb, V3 start, V3 nd, V3& pos,
                                                float& dist) {
-    float d0 = xadd(xadd(xmul(t.n.x, nd.x), xmul(t.n.y, nd.y)), xmul(t.n.z, nd.z));    // e1e2d :232
-    float d1 = xadd(xadd(xmul(be2.x, nd.x), xmul(be2.y, nd.y)), xmul(be2.z, nd.z));    // be2d  :233
-    float d2 = xadd(xadd(xmul(e1b.x, nd.x), xmul(e1b.y, nd.y)), xmul(e1b.z, nd.z));    // e1bd  :234
+    float d0 = xdot3(t.n, nd);    // e1e2d :232  ((x*x + y*y) + z*z, left to right)
+    float d1 = xdot3(be2, nd);    // be2d  :233
+    float d2 = xdot3(e1b, nd);    // e1bd  :234
     float tt = xdiv(nb, d0), u = xdiv(d1, d0), v = xdiv(d2, d0);                       // :237
     if (!(xadd(u, v) <= 1.0f && u >= 0.0f && v >= 0.0f && tt >= 0.0f)) return false;   // :239
     pos = xadd3(xadd3(t.v0, xscale3(t.e1, u)), xscale3(t.e2, v));                      // :241
