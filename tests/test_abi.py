@@ -138,3 +138,17 @@ def test_stl_loader_equals_reference_loader(pkg):
     got = pkg.load_stl(os.path.join(ref_dir, "Source", "enemy1.stl"))
     assert got.shape == want.shape == (9028, 15)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_no_packed_fma_in_the_library(pkg):
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false; the reference-order helpers
+    (csrc/exact.cuh) are written so that this pattern never arises.  No FFMA2 may appear in the SASS, and the packed
+    adds/multiplies that are used on purpose must be there."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    lib = os.path.join(ROOT, "cpp-raytracer-rasterizer_b200", "lib", "libb2r.so")
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True).stdout
+    assert "FFMA2" not in sass
+    assert "FADD2" in sass and "FMUL2" in sass
