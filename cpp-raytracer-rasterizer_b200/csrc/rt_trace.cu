@@ -527,9 +527,8 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                         if (m && !haveDir) {  // the direction is only needed by the exact test
                             // cameraRot * vec3(dx, dy, focalLength), the third products (column 2 * focalLength)
                             // taken from the frame constants                                        :580, :229
-                            nd = neg3(mk3(xadd(xadd(xmul(R[0], dx), xmul(R[3], dy)), a.fr.Rf[0]),
-                                          xadd(xadd(xmul(R[1], dx), xmul(R[4], dy)), a.fr.Rf[1]),
-                                          xadd(xadd(xmul(R[2], dx), xmul(R[5], dy)), a.fr.Rf[2])));
+                            nd = neg3(xadd3(xadd3(xscale3(mk3(R[0], R[1], R[2]), dx), xscale3(mk3(R[3], R[4], R[5]), dy)),
+                                            mk3(a.fr.Rf[0], a.fr.Rf[1], a.fr.Rf[2])));  // (col0*dx + col1*dy) + col2*f
                             haveDir = true;
                         }
                         for (; m; m &= m - 1) {  // ascending triangle index
