@@ -205,6 +205,11 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 // Lane j evaluates triangle base+j; a triangle whose form maximum is negative
 // is rejected for the whole tile and for all N*N sub-samples at once.
 // ---------------------------------------------------------------------------
+// Form k (0..2) of a pair from the interleaved table written by write_pair_constants.
+__device__ __forceinline__ V3 form_of(const float4& f0, const float4& f1, const float4& f2, int k) {
+    return k == 0 ? mk3(f0.x, f0.z, f1.x) : (k == 1 ? mk3(f0.y, f0.w, f1.y) : mk3(f1.z, f1.w, f2.x));
+}
+
 template <bool FILTER>
 __device__ __forceinline__ unsigned primary_tile_mask(const float4* __restrict__ F0, int base, int T, int lane,
                                                       float cx, float cy, float hx, float hy) {
@@ -213,9 +218,10 @@ __device__ __forceinline__ unsigned primary_tile_mask(const float4* __restrict__
     bool keep = valid;
     if (FILTER && valid) {
         const float4* F = F0 + 3 * i;
+        const float4 f0 = F[0], f1 = F[1], f2 = F[2];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float4 c = F[k];
+            const V3 c = form_of(f0, f1, f2, k);  // (B, C, A)
             const float emax = fmaf(fabsf(c.x), hx, fmaf(fabsf(c.y), hy, fmaf(c.x, cx, fmaf(c.y, cy, c.z))));
             keep = keep && !(emax < 0.f);
         }
@@ -232,12 +238,13 @@ __device__ __forceinline__ unsigned primary_ray_mask(const float4* __restrict__ 
     for (unsigned tm = tileMask; tm; tm &= tm - 1) {  // warp-uniform loop
         const int j = __ffs(tm) - 1;
         const float4* F = F0 + 3 * (base + j);
-        const float4 c1 = F[0], c2 = F[1], c3 = F[2];
-        const float E1 = fmaf(c1.x, dx, fmaf(c1.y, dy, c1.z));
-        const float E2 = fmaf(c2.x, dx, fmaf(c2.y, dy, c2.z));
-        const float E3 = fmaf(c3.x, dx, fmaf(c3.y, dy, c3.z));
+        const float4 f0 = F[0], f1 = F[1], f2 = F[2];
+        // E_k = B_k*dx + C_k*dy + A_k; forms 1 and 2 as one packed chain (two FFMA2), form 3 scalar
+        const float2 E12 = __ffma2_rn(make_float2(f0.x, f0.y), make_float2(dx, dx),
+                                      __ffma2_rn(make_float2(f0.z, f0.w), make_float2(dy, dy), make_float2(f1.x, f1.y)));
+        const float E3 = fmaf(f1.z, dx, fmaf(f1.w, dy, f2.x));
         // any sign bit set = some form negative = certain reject
-        if ((int)(__float_as_uint(E1) | __float_as_uint(E2) | __float_as_uint(E3)) >= 0) m |= 1u << j;
+        if ((int)(__float_as_uint(E12.x) | __float_as_uint(E12.y) | __float_as_uint(E3)) >= 0) m |= 1u << j;
     }
     return m;
 }
@@ -255,10 +262,11 @@ __device__ __forceinline__ unsigned shadow_warp_mask(const float4* __restrict__ 
     bool keep = valid;
     if (FILTER && valid) {
         const float4* F = Fo + 3 * i;
+        const float4 f0 = F[0], f1 = F[1], f2 = F[2];
         const float slack = kShadowMargin * rb;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const float4 g = F[k];
+            const V3 g = form_of(f0, f1, f2, k);
             const float ub = fmaxf(g.x * qlo.x, g.x * qhi.x) + fmaxf(g.y * qlo.y, g.y * qhi.y) +
                              fmaxf(g.z * qlo.z, g.z * qhi.z) + slack;
             keep = keep && !(ub < 0.f);
@@ -281,13 +289,17 @@ __device__ __forceinline__ unsigned shadow_ray_mask(const float4* __restrict__ F
     for (unsigned tm = warpMask; tm; tm &= tm - 1) {
         const int j = __ffs(tm) - 1;
         const float4* F = Fo + 3 * (base + j);
-        const float4 c1 = F[0], c2 = F[1], c3 = F[2];
-        const float G1 = fmaf(c1.x, r.x, fmaf(c1.y, r.y, fmaf(c1.z, r.z, kShadowMargin)));
-        const float G2 = fmaf(c2.x, r.x, fmaf(c2.y, r.y, fmaf(c2.z, r.z, kShadowMargin)));
-        const float G3 = fmaf(c3.x, r.x, fmaf(c3.y, r.y, fmaf(c3.z, r.z, kShadowMargin)));
+        const float4 f0 = F[0], f1 = F[1], f2 = F[2];
+        // G_k = g_k . r + margin; forms 1 and 2 as one packed chain (three FFMA2), form 3 scalar
+        const float2 G12 = __ffma2_rn(
+            make_float2(f0.x, f0.y), make_float2(r.x, r.x),
+            __ffma2_rn(make_float2(f0.z, f0.w), make_float2(r.y, r.y),
+                       __ffma2_rn(make_float2(f1.x, f1.y), make_float2(r.z, r.z), make_float2(kShadowMargin, kShadowMargin))));
+        const float G1 = G12.x, G2 = G12.y;
+        const float G3 = fmaf(f1.z, r.x, fmaf(f1.w, r.y, fmaf(f2.x, r.z, kShadowMargin)));
         if ((int)(__float_as_uint(G1) | __float_as_uint(G2) | __float_as_uint(G3)) >= 0) {
             const float Ds = (G1 + G2) + (G3 - 3.0f * kShadowMargin);
-            const bool beyond = Ds >= 4096.0f && fmaf(__fdividef(c1.w, Ds), 0.999755859375f /* 1 - 2^-12 */, -c2.w) > thr;
+            const bool beyond = Ds >= 4096.0f && fmaf(__fdividef(f2.y, Ds), 0.999755859375f /* 1 - 2^-12 */, -f2.z) > thr;
             if (!beyond) m |= 1u << j;
         }
     }
@@ -328,9 +340,11 @@ __device__ __forceinline__ void write_pair_constants(const float4* __restrict__ 
             posErr = (float)(e1n * 6.103515625e-5 /* 2^-14 */ + e0n * 9.5367431640625e-7 /* 2^-20 */);
             if (!isfinite(tnum) || !isfinite(posErr)) tnum = posErr = 0.f;
         }
-        F[0] = make_float4(q[0], q[1], q[2], tnum);
-        F[1] = make_float4(q[3], q[4], q[5], posErr);
-        F[2] = make_float4(q[6], q[7], q[8], 0.f);
+        // forms 1 and 2 interleaved, so that the per-ray filters evaluate them as one packed FMA chain (FFMA2):
+        // (f1[0], f2[0], f1[1], f2[1]) (f1[2], f2[2], f3[0], f3[1]) (f3[2], tnum, posErr, -)
+        F[0] = make_float4(q[0], q[3], q[1], q[4]);
+        F[1] = make_float4(q[2], q[5], q[6], q[7]);
+        F[2] = make_float4(q[8], tnum, posErr, 0.f);
     }
 }
 
