@@ -219,12 +219,14 @@ __device__ __forceinline__ unsigned primary_tile_mask(const float4* __restrict__
     if (FILTER && valid) {
         const float4* F = F0 + 3 * i;
         const float4 f0 = F[0], f1 = F[1], f2 = F[2];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const V3 c = form_of(f0, f1, f2, k);  // (B, C, A)
-            const float emax = fmaf(fabsf(c.x), hx, fmaf(fabsf(c.y), hy, fmaf(c.x, cx, fmaf(c.y, cy, c.z))));
-            keep = keep && !(emax < 0.f);
-        }
+        // max over the tile of E_k = |B_k|*hx + |C_k|*hy + (B_k*cx + C_k*cy + A_k); forms 1 and 2 packed, form 3 scalar
+        const float2 B12 = make_float2(f0.x, f0.y), C12 = make_float2(f0.z, f0.w);
+        const float2 e12 = __ffma2_rn(
+            make_float2(fabsf(B12.x), fabsf(B12.y)), make_float2(hx, hx),
+            __ffma2_rn(make_float2(fabsf(C12.x), fabsf(C12.y)), make_float2(hy, hy),
+                       __ffma2_rn(B12, make_float2(cx, cx), __ffma2_rn(C12, make_float2(cy, cy), make_float2(f1.x, f1.y)))));
+        const float e3 = fmaf(fabsf(f1.z), hx, fmaf(fabsf(f1.w), hy, fmaf(f1.z, cx, fmaf(f1.w, cy, f2.x))));
+        keep = !(e12.x < 0.f) && !(e12.y < 0.f) && !(e3 < 0.f);
     }
     return __ballot_sync(kFull, keep);
 }
@@ -267,8 +269,11 @@ __device__ __forceinline__ unsigned shadow_warp_mask(const float4* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const V3 g = form_of(f0, f1, f2, k);
-            const float ub = fmaxf(g.x * qlo.x, g.x * qhi.x) + fmaxf(g.y * qlo.y, g.y * qhi.y) +
-                             fmaxf(g.z * qlo.z, g.z * qhi.z) + slack;
+            // g_j * qlo_j and g_j * qhi_j side by side (FMUL2), the larger one bounds the term over the box
+            const float2 px = __fmul2_rn(make_float2(g.x, g.x), make_float2(qlo.x, qhi.x));
+            const float2 py = __fmul2_rn(make_float2(g.y, g.y), make_float2(qlo.y, qhi.y));
+            const float2 pz = __fmul2_rn(make_float2(g.z, g.z), make_float2(qlo.z, qhi.z));
+            const float ub = fmaxf(px.x, px.y) + fmaxf(py.x, py.y) + fmaxf(pz.x, pz.y) + slack;
             keep = keep && !(ub < 0.f);
         }
     }
