@@ -94,7 +94,7 @@ SYMBOLS = [
     "b2r_resolve_surface", "b2r_resolve_bgr8", "b2r_bmp_payload_bytes", "b2r_write_bmp", "b2r_rt_frame",
     "b2r_ras_frame", "b2r_set_stream", "b2r_get_stream", "b2r_synchronize", "b2r_rt_draw_device_async",
     "b2r_ras_draw_device_async", "b2r_resolve_surface_device_async", "b2r_rt_frame_device_async", "b2r_ras_frame_device_async", "b2r_rt_frame_split_device_async", "b2r_pin_host_buffer", "b2r_unpin_host_buffer", "b2r_launch_count", "b2r_get_stats",
-    "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_scene_cornell_box",
+    "b2r_enable_stats", "b2r_set_option", "b2r_measure_fp32_peak", "b2r_selftest_division", "b2r_scene_cornell_box",
     "b2r_scene_tessellate", "b2r_camera_rot_from_yaw", "b2r_orbit_camera", "b2r_jitter_table",
     "b2r_shared_alloc", "b2r_shared_free", "b2r_shared_open", "b2r_shared_close",
     "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async", "b2r_scene_load_stl",
@@ -164,6 +164,7 @@ def load_library():
     lib.b2r_enable_stats.argtypes = [vp, i32]
     lib.b2r_set_option.argtypes = [vp, i32, i32]
     lib.b2r_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.b2r_selftest_division.argtypes = [vp, C.c_ulonglong, C.c_uint, C.POINTER(C.c_ulonglong), fp]
     lib.b2r_scene_cornell_box.argtypes = [vp, i32, i32]
     lib.b2r_scene_tessellate.argtypes = [vp, i32, i32, i32, vp, i32]
     lib.b2r_scene_tessellate.restype = C.c_longlong
@@ -422,6 +423,13 @@ class Context:
         foc = np.zeros(len(p), np.float32)
         self._chk(self.lib.b2r_ras_pixel_shader_batch(self.handle, len(p), _ptr(p), _ptr(col), _ptr(nrm), _ptr(out), _ptr(foc)))
         return out, foc
+
+    def selftest_division(self, n, seed=1):
+        """(mismatches, [a, b, expected, got] of the first one) of the shared-reciprocal division against div.rn.f32."""
+        bad = C.c_ulonglong()
+        first = (C.c_float * 4)()
+        self._chk(self.lib.b2r_selftest_division(self.handle, n, seed, C.byref(bad), first))
+        return bad.value, list(first)
 
     def measure_fp32_peak(self):
         t, s = C.c_double(), C.c_double()

@@ -168,7 +168,7 @@ int b2r_destroy(b2r_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
-                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasKeys, &c->rasScratch, &c->rasSmall, &c->rtX, &c->rtF, &c->rtSched, &c->subScratch, &c->stats};
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasRefs, &c->rasScratch, &c->rasJobs, &c->rasPartials, &c->raw64, &c->rtX, &c->rtF, &c->rtSched, &c->subScratch, &c->stats};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);
@@ -215,6 +215,7 @@ int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride
     if (count) CU(cudaMemcpyAsync(c->raw.p, triangles, bytes, cudaMemcpyHostToDevice, c->stream), "scene upload");
     c->T = count;
     c->stride = stride;
+    c->rasGen++;
     // isCulled: byte 60 of the 64-byte rasteriser Triangle; the raytracer Triangle has none
     if (count) {
         if (int rc = ensure_pinned(c, (size_t)count + 64)) return rc;
@@ -223,6 +224,7 @@ int b2r_set_triangles(b2r_ctx* ctx, const void* triangles, int count, int stride
         CU(cudaMemcpyAsync(c->culled.p, m, (size_t)count, cudaMemcpyHostToDevice, c->stream), "culled upload");
     }
     CU(launch_tri_prep(c, c->stream), "tri_prep_kernel");
+    CU(launch_ras_repack(c, c->stream), "ras_repack_kernel");
     CU(cudaStreamSynchronize(c->stream), "scene upload");
     c->haveScene = true;
     return B2R_OK;
@@ -236,6 +238,7 @@ int b2r_set_culled(b2r_ctx* ctx, const uint8_t* culled, int count) {
     CU(cudaStreamSynchronize(c->stream), "sync");
     if (int rc = ensure_pinned(c, (size_t)count + 64)) return rc;
     memcpy(c->pinned, culled, (size_t)count);
+    c->rasGen++;
     CU(cudaMemcpyAsync(c->culled.p, c->pinned, (size_t)count, cudaMemcpyHostToDevice, c->stream), "culled upload");
     CU(cudaStreamSynchronize(c->stream), "culled upload");
     return B2R_OK;
@@ -297,6 +300,7 @@ int b2r_set_frame(b2r_ctx* ctx, const b2r_frame_params* p) {
             for (int i = 0; i < 3; ++i) f.origin[1 + k * samples + s][i] = src[i];
         }
     }
+    if (!c->haveFrame || memcmp(&c->params, p, sizeof *p) != 0) c->rasGen++;  // same params: same rasteriser buffer sizes
     c->params = *p;
     // pinned staging ring: a slot is reused only after its own upload has completed, so consecutive frames never
     // wait for the GPU (the copy into c->frame is stream-ordered after the kernels that still read the old frame)
@@ -319,7 +323,7 @@ int b2r_set_option(b2r_ctx* ctx, int option, int value) {
     switch (option) {
         case B2R_OPT_RT_FILTER: c->optRtFilter = value ? 1 : 0; return B2R_OK;
         case B2R_OPT_RT_VARIANT: c->optRtVariant = value; return B2R_OK;
-        case B2R_OPT_RAS_VARIANT: c->optRasVariant = value; return B2R_OK;
+        case B2R_OPT_RAS_VARIANT: c->optRasVariant = value; c->rasGen++; return B2R_OK;
         case B2R_OPT_DOF_VARIANT: c->optDofVariant = value; return B2R_OK;
     }
     return fail(c, B2R_E_INVALID, "unknown option");
@@ -605,8 +609,8 @@ static int ras_launch_band(Ctx* c, int y0, int y1, float* d_dep, float* d_col, f
     c->lastDraw = 1;
     if (y1 == y0) return B2R_OK;
     RasLaunch a;
-    a.raw = c->raw.as<unsigned char>();
-    a.stride = c->stride;
+    a.raw = c->stride == 64 ? c->raw.as<unsigned char>() : c->raw64.as<unsigned char>();
+    a.stride = 64;
     a.culled = c->culled.as<unsigned char>();
     a.T = c->T;
     a.frame = c->frame.as<DevFrame>();
@@ -721,6 +725,7 @@ int b2r_ras_cull(b2r_ctx* ctx, uint8_t* culledOut) {
     if (int rc = bind(c)) return rc;
     if (!c->haveScene || !c->haveFrame) return fail(c, B2R_E_NO_SCENE, "b2r_ras_cull needs a scene and frame params");
     CU(launch_ras_cull(c, c->culled.as<unsigned char>(), c->stream), "ras_cull_kernel");
+    c->rasGen++;
     if (culledOut && c->T)
         CU(cudaMemcpyAsync(culledOut, c->culled.p, (size_t)c->T, cudaMemcpyDeviceToHost, c->stream), "culled D2H");
     CU(cudaStreamSynchronize(c->stream), "ras_cull");

@@ -98,8 +98,8 @@ struct RasFrame {
 };
 
 struct RasLaunch {
-    const unsigned char* raw;  // reference Triangle records
-    int stride;                // 60 or 64
+    const unsigned char* raw;  // reference Triangle records, 64 bytes each (60-byte scenes are repacked at upload)
+    int stride;                // 64
     const unsigned char* culled;  // one byte per triangle (may be null => nothing culled)
     int T;
     const DevFrame* frame;
@@ -122,6 +122,7 @@ cudaError_t launch_tri_prep(Ctx* c, cudaStream_t s);
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a, cudaStream_t s);
 cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s);
 cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s);
+cudaError_t launch_ras_repack(Ctx* c, cudaStream_t s);  // 64-byte copy of a 60-byte scene for the rasteriser's 128-bit loads
 // After the stream has been synchronised: cudaErrorInvalidValue if a draw since the last call hit the row/coordinate
 // limits (-> B2R_E_CAPACITY), cudaSuccess otherwise.
 cudaError_t ras_take_error(Ctx* c);
@@ -169,6 +170,7 @@ struct Ctx {
     int T = 0;
     int stride = 0;
     DevBuf raw;      // reference Triangle records as given
+    DevBuf raw64;    // the same as 64-byte records when the caller's stride is 60 (rasteriser kernels use 128-bit loads)
     DevBuf culled;   // T bytes
     DevBuf geom;     // T * 80 bytes (raytracer)
     bool haveScene = false;
@@ -185,7 +187,7 @@ struct Ctx {
     // outputs kept on the device between draw and resolve / host copies
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
-    DevBuf rasTri, rasRows, rasKeys, rasScratch, rasSmall;
+    DevBuf rasTri, rasRows, rasRefs, rasScratch, rasJobs, rasPartials;  // triangle words + large-triangle records, edge samples, tile lists, counters
     DevBuf subScratch;  // staging of the sub-stage entry points
     struct KernelInfo {
         const void* fn;
@@ -197,8 +199,16 @@ struct Ctx {
     void* waitValue32 = nullptr;  // cuStreamWaitValue32 when the driver offers stream memory operations
     bool memOpsProbed = false;
     DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
-    size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
-    void* rasKeysCleanPtr = nullptr;
+    size_t rasTilesClean = 0;         // tile counts known to be zero for a grid of this many tiles (left so by ras_tile)
+    // Buffer sizes of the rasteriser's large-scene path, read back once per (scene, culling flags, frame params, band):
+    // rasGen counts the changes of the first three.
+    unsigned long long rasGen = 1;
+    struct RasSizes {
+        bool valid = false;
+        unsigned long long gen = 0;
+        int y0 = 0, y1 = 0;
+        unsigned nBig = 0, bigSamples = 0, totalRefs = 0;
+    } rasSizes;
     // pinned staging for host-pointer entry points
     void* pinned = nullptr;
     size_t pinnedCap = 0;

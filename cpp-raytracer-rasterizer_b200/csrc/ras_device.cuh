@@ -24,6 +24,14 @@ __device__ __forceinline__ float xdiv_step(float a, float b) {
     return xdiv(a, b);
 }
 
+// the same with the reciprocal of b shared between several numerators (see Recip in exact.cuh)
+__device__ __forceinline__ float xdiv_step_by(float a, const Recip& d) {
+    if (d.b == 1.0f) return a;
+    if (a == 0.0f && d.b != 0.0f && d.b == d.b)
+        return __int_as_float((__float_as_int(a) ^ __float_as_int(d.b)) & 0x80000000);
+    return xdiv_by(a, d);
+}
+
 struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
     int x, y;
     float zinv;
@@ -31,13 +39,22 @@ struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
 };
 
 // f: frame constants in the kernel-parameter bank (uniform loads, no global traffic per vertex)
+// SHARED: the three divisions by pos.z share one reciprocal (frame pipeline); the plain form is what the sub-stage
+// entry points run, so the two are checked against each other through the reference's vectors.
+template <bool SHARED = false>
 __device__ __forceinline__ RPixel vertex_shader(const RasFrame& f, V3 v) {
     RPixel p;
     V3 pos = xvec_mat(xsub3(v, mk3(f.cam[0], f.cam[1], f.cam[2])), f.R);       // :535
     // :538 pos / pos.z; the z component is x/x == 1.0f exactly for every finite non-zero x
     const bool plain = pos.z != 0.0f && fabsf(pos.z) <= 3.402823466e+38f;
-    p.p = mk3(xdiv(pos.x, pos.z), xdiv(pos.y, pos.z), plain ? 1.0f : xdiv(pos.z, pos.z));
-    p.zinv = xdiv(1.0f, pos.z);                                                 // :541
+    if (SHARED) {
+        const Recip d = recip_make(pos.z);
+        p.p = mk3(xdiv_by(pos.x, d), xdiv_by(pos.y, d), plain ? 1.0f : xdiv(pos.z, pos.z));
+        p.zinv = xdiv_by(1.0f, d);                                              // :541
+    } else {
+        p.p = mk3(xdiv(pos.x, pos.z), xdiv(pos.y, pos.z), plain ? 1.0f : xdiv(pos.z, pos.z));
+        p.zinv = xdiv(1.0f, pos.z);                                             // :541
+    }
     float fx = xmul(f.focal, xmul(pos.x, p.zinv));
     float fy = xmul(f.focal, xmul(pos.y, p.zinv));
     p.x = f2i_x86(xadd(__int2float_rn(f2i_x86(fx)), f.halfW));                 // :544  + (SCREEN_WIDTH / 2.0f)
@@ -47,11 +64,18 @@ __device__ __forceinline__ RPixel vertex_shader(const RasFrame& f, V3 v) {
 
 
 // PixelShader (rasteriser.cpp:549-589) for one fragment with interpolated zinv / pos3d.
+template <bool SHARED = false>
 __device__ __forceinline__ void pixel_shader_core(const RasFrame& fr, float zinv, V3 pos3d, V3 normal, V3 color,
                                                   float& focal, V3& colour) {
     const RasFrame* f = &fr;
     const V3 cam = mk3(f->cam[0], f->cam[1], f->cam[2]);
-    V3 P = xdivs3(pos3d, zinv);        // :557
+    V3 P;                              // :557 pos3d / zinv
+    if (SHARED) {
+        const Recip d = recip_make(zinv);
+        P = mk3(xdiv_by(pos3d.x, d), xdiv_by(pos3d.y, d), xdiv_by(pos3d.z, d));
+    } else {
+        P = xdivs3(pos3d, zinv);
+    }
     P = xvec_mat(P, f->Rinv);          // :559
     P = xadd3(P, cam);                 // :560
     const V3 dc = xsub3(cam, P);       // glm::distance(pPos3d, cameraPos) = length(cameraPos - pPos3d)

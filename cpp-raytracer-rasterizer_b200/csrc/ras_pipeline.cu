@@ -9,31 +9,39 @@
 // `zinv > depthBuffer` test against a buffer cleared to 0 (:606, :188).  The
 // final image therefore only depends on, per pixel, the fragment with the
 // largest zinv, the lowest triangle index among exact ties, and only
-// fragments with zinv > 0.  A 64-bit key (zinv bits << 32 | ~index) and an
-// atomicMax reproduce that for any execution order; shading is deferred to
-// the winner (PixelShader's writes are simply overwritten by later winners in
-// the reference, so shading only the final one gives identical arrays).
+// fragments with zinv > 0.  That rule is order-free, so the frame is built
+// sort-middle: triangles are binned to 32x32 screen tiles and one CTA per tile
+// resolves depth and ownership in shared memory, then runs PixelShader once per
+// pixel for the winner (PixelShader's writes are simply overwritten by later
+// winners in the reference, so shading only the final one gives identical arrays).
 //
 // All arithmetic that decides coverage, depth or colour is in reference order,
 // non-fused.  Interpolate's serial float accumulation along each edge (:632-635)
 // decides both coverage (via int(current.x)) and the zinv values compared in the
 // depth test, so it is replayed step by step, never re-associated.
 //
-// Pipeline (v2):
-//   ras_small     1 thread / triangle.  VertexShader x3.  Triangles of <= 20 rows
-//                 (the 1M-triangle regime) are finished here: the three edge walks
-//                 update per-row left/right ends kept in shared memory, then every
-//                 on-screen fragment goes to the key buffer with atomicMax.  The only
-//                 intermediate that reaches HBM is one 32-byte row record per polygon
-//                 row (fixed slot, no allocation pass).  Larger triangles are appended
-//                 to a compact list (setup record + row/edge-sample counts).
-//   big path      only for the listed large triangles: exclusive scan of the counts,
-//                 ras_edges (1 thread / triangle-edge, stores every edge sample),
-//                 ras_rows (1 lane / polygon row; short rows per lane, long rows
-//                 cooperatively across the warp).
-//   ras_shade     1 thread / pixel, streaming: key -> winner -> its row record ->
-//                 PixelShader in reference order, coalesced writes; clears the key.
+// Pipeline:
+//   ras_setup     1 thread / triangle: VertexShader x3, row count, conservative tile rectangle, per-tile
+//                 reference counts.  Triangles of more than 20 rows (or wider than 128 tiles) go to the
+//                 large-triangle list, whose edge walks are done once by ras_edges into HBM.
+//                 The last CTA to finish turns the counts into list offsets (exclusive scan).
+//   ras_bin       1 thread / triangle: writes the triangle into the list of every tile of its rectangle; lanes
+//                 of a warp that hit the same tile share one atomic (match + prefix popcount).
+//   ras_edges     large triangles only: 1 thread / (triangle, edge, chain), stores every edge sample.
+//   ras_tile      1 CTA / tile, everything in shared memory:
+//                   A1  1 thread / listed triangle: VertexShader x3 again (cheaper than a 60-byte round trip
+//                       through HBM), rows inside the tile, block prefix sum -> row items
+//                   W   1 thread / (triangle, edge): Interpolate's serial walk, samples of the tile's rows kept
+//                   A3  1 thread / row item: ComputePolygonRows' left/right resolve, DrawLineSDL's span clipped
+//                       to the tile, atomicMax of the zinv bits on the 32-bit depth tile
+//                   B1  same thread: fragments that hold the final depth take atomicMin(owner, triangle index)
+//                   B2  same thread: the owning fragment leaves its interpolated pos3d.xy for the pixel
+//                   C   1 thread / pixel: PixelShader of the winner, coalesced stores of depth / colour / ...
+//                 The 64-bit (depth, index) order is thus resolved with native 32-bit shared-memory atomics;
+//                 no key, span or row record ever reaches HBM.
 #include <limits.h>
+
+#include <algorithm>
 
 #include "b2r_internal.h"
 #include "exact.cuh"
@@ -42,251 +50,287 @@
 
 namespace b2r {
 
-struct TriSetup {  // 24 words
-    int vx[3], vy[3];
-    float vz[3];
-    float vp[9];
-    int minY, rows;
-    unsigned rowBase, sampleBase;
-    int drawn, tri;  // tri = index in the caller's triangle array (draw order)
-};
-
-struct EdgeSample {  // 5 words
-    int x;
-    float zinv;
-    float p[3];
-};
-
-struct RowRec {  // 12 words: left/right ends of one polygon row (y implied)
-    int lx, rx;
-    float lz, rz;
-    float lp[3], rp[3];
-    int pad[2];
-};
+constexpr int kTileShift = 5;
+constexpr int kTileW = 1 << kTileShift, kTileH = 1 << kTileShift, kTilePix = kTileW * kTileH;
+constexpr int kTileThreads = 256;
+constexpr int kSmallRows = 20;          // triangles up to this many polygon rows are walked inside ras_tile
+constexpr int kMaxSmallTilesX = 128;    // ... unless they are wider than this many tiles
+constexpr unsigned kBigRef = 0x80000000u;  // tile-list entry / triWord: large-triangle slot in the low bits
+constexpr unsigned kNoRect = 0x7FFFFFFFu;  // triWord: nothing to draw (culled, off screen, outside the band)
+constexpr unsigned kSmallTri = 0xFFFFFFFFu;
+constexpr int kSlice = 512;             // tile-list entries per job (CTA) of ras_tile; longer lists are split and merged
 
 constexpr int kMaxRowsPerTriangle = 1 << 22;
 constexpr int kCoordLimit = 1 << 24;
 
-// ---- stage 1: setup, classification, and the complete small-triangle path ----------------------
-constexpr int kSmallRows = 20;      // triangles up to this many polygon rows are finished by ras_small
-constexpr int kWindowRows = 7;      // rows whose ends are held in shared memory at a time (one walk per window)
-constexpr int kSmallThreads = 128;
+// Large triangle: projected vertices (VertexShader output), where its edge samples live, its tile rectangle.
+// pos3d.z is omitted everywhere: it is pos.z/pos.z == 1.0f exactly for every triangle that passes the coordinate
+// limits (a NaN there makes x,y INT_MIN -> B2R_E_CAPACITY), Interpolate's z step is then (1-1)/n == 0 and
+// Bresenham's is 0/pixels == 0, so that chain is 1.0f for every fragment.
+struct TriSetup {  // 24 words
+    int vx[3], vy[3];
+    float vz[3], vpx[3], vpy[3];
+    int minY, rows;
+    unsigned sampleBase;
+    int tri;  // index in the caller's triangle array (draw order)
+    int tx0, tx1, ty0, ty1;
+    int pad;
+};
+
+struct EdgeSample {  // one Interpolate() result entry (:628-631) without y (implied) and pos3d.z (== 1)
+    int x;
+    float zinv, px, py;
+};
 
 struct RasCounters {
-    unsigned nBig, bigRows, bigSamples, err;
+    unsigned nBig, bigRows, bigSamples, err, totalRefs, blocksDone, totalJobs, pad0;  // per frame, re-armed by ras_tile
     unsigned sticky;  // like err, but only cleared by the host after it has been reported (asynchronous draws)
-    unsigned pad;
+    unsigned pad1[7];
 };
 
-// Row ends of one polygon row of a small triangle, written by ras_small for the shade pass: 32 bytes at the
-// fixed slot (triangle * kSmallRows + row), so no allocation pass is needed.  pos3d.z is omitted: it is
-// pos.z/pos.z == 1.0f exactly for every triangle that passes the coordinate limits, and Interpolate's z step is
-// then (1-1)/n == 0, so that chain stays 1.0f.
-struct SmallRow {
-    int lx, rx;
-    float lz, rz;
-    float lpx, lpy, rpx, rpy;
-};
-
-// Depth key: larger zinv wins, then the lower triangle index (the reference's strict `>` in draw order, :606).
-// Bit 0 tells the shade pass which kind of row record the winner has; it cannot affect the order because it is
-// a function of the triangle index in the bits above it.  Triangle indices are below 2^31.
-__device__ __forceinline__ unsigned long long pack_key(float zinv, unsigned tri, unsigned big) {
-    return ((unsigned long long)__float_as_uint(zinv) << 32) | (unsigned long long)(((0x7FFFFFFFu - tri) << 1) | big);
-}
-__device__ __forceinline__ unsigned key_triangle(unsigned long long key) { return 0x7FFFFFFFu - ((unsigned)key >> 1); }
-// slot of polygon row y of small triangle tri: a small triangle spans at most kSmallRows consecutive rows,
-// so y modulo kSmallRows is unique within it
-__device__ __forceinline__ size_t small_row_slot(unsigned tri, int y) {
-    int m = y % kSmallRows;
-    if (m < 0) m += kSmallRows;
-    return (size_t)tri * kSmallRows + (size_t)m;
+// How far int(current.x) of an edge walk can lie outside the vertices' x range: the chain a.x + step + step + ...
+// drifts from the exact line by at most one ulp of the largest magnitude per step (half from the addition, half
+// from the rounded step), plus the truncation.
+__device__ __forceinline__ int coord_margin(int steps, int maxAbs) {
+    return 2 + (int)((float)steps * (float)maxAbs * 2.4e-7f);  // 2^-22 = 2.38e-7
 }
 
-// One edge of Interpolate (:615-637): the x and zinv chains decide coverage and depth, the pos3d.xy chains
-// feed PixelShader (pos3d.z stays 1.0f, see SmallRow).
-struct EdgeStep {
-    int n, sgn;
-    float cx, cz, cpx, cpy, sx, sz, spx, spy;
-};
-__device__ __forceinline__ EdgeStep edge_begin(const RPixel& a, const RPixel& b) {
-    EdgeStep e;
-    e.n = abs(a.y - b.y) + 1;                            // :712
-    e.sgn = (b.y > a.y) - (b.y < a.y);
-    const float div = (float)max(e.n - 1, 1);            // :622
-    e.sx = xdiv_step((float)(b.x - a.x), div);           // Pixel operator- / fPixel operator/
-    e.sz = xdiv_step(xsub(b.zinv, a.zinv), div);
-    e.spx = xdiv_step(xsub(b.p.x, a.p.x), div);
-    e.spy = xdiv_step(xsub(b.p.y, a.p.y), div);
-    e.cx = (float)a.x;                                   // fPixel(Pixel&)
-    e.cz = a.zinv;
-    e.cpx = a.p.x;
-    e.cpy = a.p.y;
-    return e;
+// The three vertices: 9 floats at the head of the 64-byte record (b2r_set_triangles repacks 60-byte scenes once), three
+// 128-bit loads.
+__device__ __forceinline__ void load_vertices(const RasLaunch& a, int i, float* t /* 12 */) {
+    const float4* q = reinterpret_cast<const float4*>(a.raw + (size_t)i * 64);
+    const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+    t[0] = q0.x; t[1] = q0.y; t[2] = q0.z; t[3] = q0.w; t[4] = q1.x; t[5] = q1.y; t[6] = q1.z; t[7] = q1.w;
+    t[8] = q2.x; t[9] = q2.y; t[10] = q2.z; t[11] = q2.w;
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a, unsigned long long* __restrict__ keys,
-                                                                   TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
-                                                                   int2* __restrict__ triInfo, SmallRow* __restrict__ rowRec,
-                                                                   RasCounters* __restrict__ ctr) {
-    // per-thread row ends, [row][field][thread] so that a warp's accesses never conflict
-    extern __shared__ int srow[];
-    int* const mine = srow + threadIdx.x;
-    float* const minef = reinterpret_cast<float*>(mine);
-    auto LX = [&](int r) -> int& { return mine[(8 * r + 0) * kSmallThreads]; };
-    auto RX = [&](int r) -> int& { return mine[(8 * r + 1) * kSmallThreads]; };
-    auto LZ = [&](int r) -> float& { return minef[(8 * r + 2) * kSmallThreads]; };
-    auto RZ = [&](int r) -> float& { return minef[(8 * r + 3) * kSmallThreads]; };
-    auto LPX = [&](int r) -> float& { return minef[(8 * r + 4) * kSmallThreads]; };
-    auto LPY = [&](int r) -> float& { return minef[(8 * r + 5) * kSmallThreads]; };
-    auto RPX = [&](int r) -> float& { return minef[(8 * r + 6) * kSmallThreads]; };
-    auto RPY = [&](int r) -> float& { return minef[(8 * r + 7) * kSmallThreads]; };
+// ---- stage 1: set-up, classification, per-tile counts; stage 2 (tile offsets) in its last block ----
+// Lanes of a warp that touch the same tile share one atomic: __match_any_sync groups them and the group's first lane
+// adds popc(group).
+__device__ __forceinline__ void count_tile(unsigned* __restrict__ tileCount, int tile, int lane) {
+    const unsigned peers = __match_any_sync(__activemask(), tile);
+    if (lane == __ffs(peers) - 1) atomicAdd(&tileCount[tile], (unsigned)__popc(peers));
+}
 
-    const int i = blockIdx.x * kSmallThreads + threadIdx.x;
-    unsigned long long nTests = 0, nRows = 0, nDrawn = 0;
-    if (i < a.T && !(a.culled && a.culled[i])) {  // :470
-        // the three vertices: 9 floats at the head of the record; 64-byte records (the rasteriser's Triangle) are
-        // 16-byte aligned and are fetched with three 128-bit loads instead of nine 32-bit ones
-        float t[12];
-        if (a.stride == 64) {
-            const float4* q = reinterpret_cast<const float4*>(a.raw + (size_t)i * 64);
-            const float4 q0 = q[0], q1 = q[1], q2 = q[2];
-            t[0] = q0.x; t[1] = q0.y; t[2] = q0.z; t[3] = q0.w; t[4] = q1.x; t[5] = q1.y; t[6] = q1.z; t[7] = q1.w;
-            t[8] = q2.x; t[9] = q2.y; t[10] = q2.z; t[11] = q2.w;
-        } else {
-            const float* r = reinterpret_cast<const float*>(a.raw + (size_t)i * a.stride);
+// One CTA of 256 threads, each owning a contiguous run of tiles: exclusive scan of the per-tile counts (list offsets) and
+// the job table of ras_tile -- a tile whose list is longer than kSlice entries is drawn by several CTAs (jobs), each
+// taking kSlice entries, which meet in a partial-result buffer (slot mslot + slice).  The counts are zeroed on the way
+// (ras_bin uses them as cursors).  tileOffset[nTiles] = total entries, tileOffset[nTiles + 1] = total jobs.
+// FROM_OFFSETS: only the job table and the partial slots are (re)built, from offsets that are already there.
+template <bool FROM_OFFSETS>
+__device__ void tile_scan_block(unsigned* __restrict__ tileCount, unsigned* __restrict__ tileOffset, unsigned* __restrict__ tileMslot,
+                                uint2* __restrict__ jobTile, unsigned jobCap, int nTiles, RasCounters* __restrict__ ctr) {
+    __shared__ unsigned warpSums[3][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (nTiles + 255) / 256, t0 = min(tid * per, nTiles), t1 = min(t0 + per, nTiles);
+    unsigned sum[3] = {0u, 0u, 0u};  // entries, jobs, partial slots
+    for (int t = t0; t < t1; ++t) {
+        const unsigned v = FROM_OFFSETS ? __ldcg(&tileOffset[t + 1]) - __ldcg(&tileOffset[t]) : __ldcg(&tileCount[t]);
+        const unsigned k = max(1u, (v + kSlice - 1) / kSlice);
+        sum[0] += v;
+        sum[1] += k;
+        sum[2] += (k > 1u) ? k : 0u;
+    }
+    unsigned run[3];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) t[k] = r[k];
+    for (int c = 0; c < 3; ++c) {
+        unsigned inc = sum[c];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned x = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += x;
         }
+        if (lane == 31) warpSums[c][warp] = inc;
+        run[c] = inc - sum[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < warp) run[c] += warpSums[c][k];
+    for (int t = t0; t < t1; ++t) {
+        unsigned v;
+        if (FROM_OFFSETS) {
+            v = __ldcg(&tileOffset[t + 1]) - __ldcg(&tileOffset[t]);
+        } else {
+            v = __ldcg(&tileCount[t]);
+            tileOffset[t] = run[0];
+            tileCount[t] = 0u;
+        }
+        const unsigned k = max(1u, (v + kSlice - 1) / kSlice);
+        tileMslot[t] = run[2];
+        for (unsigned sl = 0; sl < k; ++sl)
+            if (run[1] + sl < jobCap) jobTile[run[1] + sl] = make_uint2((unsigned)t, sl);  // a short table is rebuilt by ras_jobs
+        run[0] += v;
+        run[1] += k;
+        run[2] += (k > 1u) ? k : 0u;
+    }
+    if (tid == 255) {
+        if (!FROM_OFFSETS) {
+            tileOffset[nTiles] = run[0];
+            ctr->totalRefs = run[0];
+            ctr->totalJobs = run[1];
+        }
+        tileOffset[nTiles + 1] = run[1];
+    }
+}
+
+// Rebuilds the job table after the host has sized it (first frame of a new scene / camera / band only).
+__global__ void __launch_bounds__(256) ras_jobs_kernel(unsigned* tileOffset, unsigned* tileMslot, uint2* jobTile, unsigned jobCap,
+                                                       int nTiles) {
+    tile_scan_block<true>(nullptr, tileOffset, tileMslot, jobTile, jobCap, nTiles, nullptr);
+}
+
+__global__ void __launch_bounds__(256) ras_setup_kernel(RasLaunch a, int tilesX, int nTiles, unsigned* __restrict__ triWord,
+                                                        TriSetup* __restrict__ bigTs, uint2* __restrict__ bigCounts,
+                                                        unsigned* __restrict__ tileCount, unsigned* __restrict__ tileOffset,
+                                                        unsigned* __restrict__ tileMslot, uint2* __restrict__ jobTile,
+                                                        unsigned jobCap, RasCounters* __restrict__ ctr) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned word = kNoRect;
+    unsigned long long nRows = 0, nDrawn = 0;
+    int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+    bool big = false;
+    float t[12];
+    unsigned char isCulled = 1;
+    if (i < a.T) {  // both loads in flight together: the flag does not gate the vertex fetch
+        isCulled = a.culled ? a.culled[i] : (unsigned char)0;
+        load_vertices(a, i, t);
+    }
+    if (!isCulled) {  // :470
         RPixel v[3];
-        int maxY = INT_MIN, minY = INT_MAX;
+        int maxY = INT_MIN, minY = INT_MAX, maxX = INT_MIN, minX = INT_MAX;
         bool bad = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            v[k] = vertex_shader(a.fr, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]));  // :760-761
+            v[k] = vertex_shader<true>(a.fr, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]));  // :760-761
             maxY = max(maxY, v[k].y);
             minY = min(minY, v[k].y);
+            maxX = max(maxX, v[k].x);
+            minX = min(minX, v[k].x);
             bad = bad || v[k].x <= -kCoordLimit || v[k].x >= kCoordLimit || v[k].y <= -kCoordLimit || v[k].y >= kCoordLimit;
         }
         const int rows = maxY - minY + 1;  // :682
         if (bad || rows > kMaxRowsPerTriangle) {
             atomicExch(&ctr->err, 1u);  // the reference would try to allocate/walk an absurd row count
             atomicExch(&ctr->sticky, 1u);
-        } else if (rows > kSmallRows) {
-            const unsigned samples = (unsigned)(abs(v[0].y - v[1].y) + abs(v[1].y - v[2].y) + abs(v[2].y - v[0].y) + 3);
-            const unsigned slot = atomicAdd(&ctr->nBig, 1u);
-            atomicAdd(&ctr->bigRows, (unsigned)rows);
-            atomicAdd(&ctr->bigSamples, samples);
-            TriSetup s;
-            for (int k = 0; k < 3; ++k) {
-                s.vx[k] = v[k].x;
-                s.vy[k] = v[k].y;
-                s.vz[k] = v[k].zinv;
-                s.vp[3 * k] = v[k].p.x;
-                s.vp[3 * k + 1] = v[k].p.y;
-                s.vp[3 * k + 2] = v[k].p.z;
-            }
-            s.minY = minY;
-            s.rows = rows;
-            s.rowBase = s.sampleBase = 0;
-            s.drawn = 1;
-            s.tri = i;
-            if (a.bandSlots) {
-                // fixed-capacity slots: only rows of the band are kept, so a triangle needs at most bandH row
-                // records and bandH samples per edge; rows are addressed by y - y0 (no scan, no readback)
-                const unsigned bandH = (unsigned)(a.y1 - a.y0);
-                s.rowBase = slot * bandH;
-                s.sampleBase = slot * 3u * bandH;
-                bigTs[slot] = s;
-                triInfo[i] = make_int2((int)slot, a.y0);
-            } else {
-                bigTs[slot] = s;
-                bigCounts[slot] = make_uint2((unsigned)rows, samples);
-                triInfo[i] = make_int2((int)slot, minY);
-            }
-            nDrawn = 1;
-            nRows = (unsigned long long)rows;
         } else {
             nDrawn = 1;
             nRows = (unsigned long long)rows;
-            const int r0 = max(0, a.y0 - minY), r1 = min(rows, a.y1 - minY);  // rows of this band (DrawRows :743)
-            // Row ends live in shared memory for kWindowRows rows at a time; a triangle with more rows replays its
-            // edge walks once per window (86 % of config 4's triangles need one window).  The accumulation itself
-            // always runs over every step -- only the stores are windowed -- so the values are unchanged.
-            for (int w0 = 0; w0 < rows; w0 += kWindowRows) {
-                const int w1 = min(rows, w0 + kWindowRows);
-                const int e0 = max(w0, r0), e1 = min(w1, r1);  // rows of this window that are in the band
-                if (e0 >= e1) continue;
-                for (int r = 0; r < w1 - w0; ++r) {  // :694-698
-                    LX(r) = INT_MAX;
-                    RX(r) = -INT_MAX;
-                }
-                // ComputePolygonRows: edges 0->1, 1->2, 2->0 in order, strict </> so the first edge to
-                // reach an extreme x keeps its attributes (:705-733)
+            // conservative rectangle of the fragments (x = lx+1 .. rx of every row), clipped to the screen and the band
+            const int m = coord_margin(rows, max(abs(minX), abs(maxX)));
+            const int xa = max(minX - m, 0), xb = min(maxX + m, a.W - 1);
+            const int ya = max(minY, a.y0), yb = min(maxY, a.y1 - 1);  // DrawRows :743 + the band
+            if (xa <= xb && ya <= yb) {
+                tx0 = xa >> kTileShift;
+                tx1 = xb >> kTileShift;
+                ty0 = (ya - a.y0) >> kTileShift;
+                ty1 = (yb - a.y0) >> kTileShift;
+                big = rows > kSmallRows || tx1 - tx0 >= kMaxSmallTilesX;
+                if (big) {
+                    const unsigned samples = (unsigned)(abs(v[0].y - v[1].y) + abs(v[1].y - v[2].y) + abs(v[2].y - v[0].y) + 3);
+                    const unsigned slot = atomicAdd(&ctr->nBig, 1u);
+                    atomicAdd(&ctr->bigRows, (unsigned)rows);
+                    atomicAdd(&ctr->bigSamples, samples);
+                    TriSetup s;
 #pragma unroll
-                for (int e = 0; e < 3; ++e) {
-                    const int j = (e + 1) % 3;
-                    EdgeStep st = edge_begin(v[e], v[j]);
-                    int r = v[e].y - minY - w0;
-                    for (int k = 0; k < st.n; ++k) {  // :626-636, serial accumulation
-                        if ((unsigned)r < (unsigned)(w1 - w0)) {
-                            // int(current.x): the chain stays within one pixel of the vertex range, which passed
-                            // the +-2^24 limit, so the plain truncating conversion equals the x86 one
-                            const int x = __float2int_rz(st.cx);
-                            if (x < LX(r)) {
-                                LX(r) = x;
-                                LZ(r) = st.cz;
-                                LPX(r) = st.cpx;
-                                LPY(r) = st.cpy;
-                            }
-                            if (x > RX(r)) {
-                                RX(r) = x;
-                                RZ(r) = st.cz;
-                                RPX(r) = st.cpx;
-                                RPY(r) = st.cpy;
-                            }
-                        }
-                        st.cx = xadd(st.cx, st.sx);
-                        st.cz = xadd(st.cz, st.sz);
-                        st.cpx = xadd(st.cpx, st.spx);
-                        st.cpy = xadd(st.cpy, st.spy);
-                        r += st.sgn;
+                    for (int k = 0; k < 3; ++k) {
+                        s.vx[k] = v[k].x;
+                        s.vy[k] = v[k].y;
+                        s.vz[k] = v[k].zinv;
+                        s.vpx[k] = v[k].p.x;
+                        s.vpy[k] = v[k].p.y;
                     }
-                }
-                // DrawRows / DrawLineSDL / Bresenham with dy == 0 (:738-753, :592-612, :639-672)
-                for (int rr = e0; rr < e1; ++rr) {
-                    const int r = rr - w0;
-                    const int lx = LX(r), rx = RX(r), pixels = rx - lx;  // :598
-                    const float lz = LZ(r), rz = RZ(r);
-                    {   // one full 32-byte sector per row, for the shade pass
-                        float4* rec = reinterpret_cast<float4*>(rowRec + small_row_slot((unsigned)i, minY + rr));
-                        rec[0] = make_float4(__int_as_float(lx), __int_as_float(rx), lz, rz);
-                        rec[1] = make_float4(LPX(r), LPY(r), RPX(r), RPY(r));
-                    }
-                    const int i0 = max(0, -lx - 1), i1 = min(pixels, a.W - lx - 1);  // :663 keeps 0 <= x < W
-                    if (i1 <= i0) continue;  // no fragment (incl. pixels == 0, whose 0/0 step nobody reads)
-                    const float zstep = xdiv_step(xsub(rz, lz), (float)pixels);  // :648 (constant-depth rows: 0/n)
-                    unsigned long long* keyRow = keys + (size_t)(minY + rr - a.y0) * (size_t)a.W;
-                    for (int q = i0; q < i1; ++q) {
-                        const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
-                        if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
-                            atomicMax(keyRow + (lx + 1 + q), pack_key(zinv, (unsigned)i, 0u));
-                    }
-                    nTests += (unsigned long long)(i1 - i0);
+                    s.minY = minY;
+                    s.rows = rows;
+                    // fixed-capacity slots (small scenes): only rows of the band are kept, bandH samples per edge,
+                    // addressed by y - y0 (no scan, no readback); otherwise the scan fills sampleBase in
+                    s.sampleBase = a.bandSlots ? slot * 3u * (unsigned)(a.y1 - a.y0) : 0u;
+                    s.tri = i;
+                    s.tx0 = tx0; s.tx1 = tx1; s.ty0 = ty0; s.ty1 = ty1;
+                    s.pad = 0;
+                    bigTs[slot] = s;
+                    if (!a.bandSlots) bigCounts[slot] = make_uint2((unsigned)rows, samples);
+                    word = kBigRef | slot;
+                } else {
+                    word = (unsigned)tx0 | ((unsigned)ty0 << 10) | ((unsigned)(tx1 - tx0) << 20) | ((unsigned)(ty1 - ty0) << 27);
+                    for (int ty = ty0; ty <= ty1; ++ty)
+                        for (int tx = tx0; tx <= tx1; ++tx) count_tile(tileCount, ty * tilesX + tx, lane);
                 }
             }
         }
     }
+    if (i < a.T) triWord[i] = word;
+    // large triangles: the warp counts the tiles of each rectangle together
+    unsigned bigMask = __ballot_sync(0xffffffffu, big);
+    while (bigMask) {
+        const int src = __ffs(bigMask) - 1;
+        bigMask &= bigMask - 1;
+        const int bx0 = __shfl_sync(0xffffffffu, tx0, src), bx1 = __shfl_sync(0xffffffffu, tx1, src);
+        const int by0 = __shfl_sync(0xffffffffu, ty0, src), by1 = __shfl_sync(0xffffffffu, ty1, src);
+        const int w = bx1 - bx0 + 1, n = w * (by1 - by0 + 1);
+        for (int k = lane; k < n; k += 32) atomicAdd(&tileCount[(by0 + k / w) * tilesX + bx0 + k % w], 1u);
+    }
     if (a.stats) {
         for (int off = 16; off > 0; off >>= 1) {
-            nTests += __shfl_xor_sync(0xffffffffu, nTests, off);
             nRows += __shfl_xor_sync(0xffffffffu, nRows, off);
             nDrawn += __shfl_xor_sync(0xffffffffu, nDrawn, off);
         }
-        if ((threadIdx.x & 31) == 0) {
-            if (nTests) atomicAdd(a.stats + B2R_STAT_RAS_DEPTH_TESTS, nTests);
+        if (lane == 0) {
             if (nRows) atomicAdd(a.stats + B2R_STAT_RAS_ROWS, nRows);
             if (nDrawn) atomicAdd(a.stats + B2R_STAT_RAS_TRIANGLES, nDrawn);
+        }
+    }
+    // the last CTA to get here turns the tile counts into list offsets (no separate launch)
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(&ctr->blocksDone, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (isLast) {
+        __threadfence();
+        tile_scan_block<false>(tileCount, tileOffset, tileMslot, jobTile, jobCap, nTiles, ctr);
+    }
+}
+
+// ---- stage 3: binning -------------------------------------------------------------------------------
+// Lanes of a warp that append to the same tile list share one atomicAdd: __match_any_sync groups them, the group's
+// first lane reserves popc(group) entries and each lane's position is the prefix popcount of the group below it.
+__device__ __forceinline__ void bin_append(unsigned* __restrict__ cursor, const unsigned* __restrict__ tileOffset,
+                                           unsigned* __restrict__ refs, int tile, unsigned entry, int lane) {
+    const unsigned peers = __match_any_sync(__activemask(), tile);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&cursor[tile], (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    refs[tileOffset[tile] + base + (unsigned)__popc(peers & ((1u << lane) - 1u))] = entry;
+}
+
+__global__ void __launch_bounds__(256) ras_bin_kernel(const unsigned* __restrict__ triWord, int T, int tilesX,
+                                                      const TriSetup* __restrict__ bigTs, unsigned* __restrict__ cursor,
+                                                      const unsigned* __restrict__ tileOffset, unsigned* __restrict__ refs) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned w = (i < T) ? triWord[i] : kNoRect;
+    const bool big = (w & kBigRef) != 0u;
+    if (!big && w != kNoRect) {
+        const int tx0 = (int)(w & 1023u), ty0 = (int)((w >> 10) & 1023u);
+        const int nx = (int)((w >> 20) & 127u) + 1, ny = (int)((w >> 27) & 15u) + 1;
+        for (int dy = 0; dy < ny; ++dy)
+            for (int dx = 0; dx < nx; ++dx) bin_append(cursor, tileOffset, refs, (ty0 + dy) * tilesX + tx0 + dx, (unsigned)i, lane);
+    }
+    unsigned bigMask = __ballot_sync(0xffffffffu, big);
+    while (bigMask) {
+        const int src = __ffs(bigMask) - 1;
+        bigMask &= bigMask - 1;
+        const unsigned entry = __shfl_sync(0xffffffffu, w, src);
+        const TriSetup* s = bigTs + (entry & ~kBigRef);
+        const int bx0 = s->tx0, by0 = s->ty0, bw = s->tx1 - bx0 + 1, n = bw * (s->ty1 - by0 + 1);
+        for (int k = lane; k < n; k += 32) {  // distinct tiles per lane: plain atomics
+            const int tile = (by0 + k / bw) * tilesX + bx0 + k % bw;
+            refs[tileOffset[tile] + atomicAdd(&cursor[tile], 1u)] = entry;
         }
     }
 }
@@ -351,27 +395,22 @@ __global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __r
     int i = blockIdx.x * kScanBlock + threadIdx.x;
     if (i >= n) return;
     uint2 o = add2(ex[i], blockSums[blockIdx.x]);
-    ts[i].rowBase = o.x;
     ts[i].sampleBase = o.y;
 }
 
-// ---- stage 2: Interpolate (:615-637), one thread per (triangle, edge) --------
-// One thread per (triangle, edge, chain): the five accumulation chains of an edge (x, zinv, pos3d.xyz) are
-// independent of each other, so each runs its own serial loop -- 15 threads per triangle instead of 3 -- and writes
-// its field of every sample.  A 2160-row edge is latency-bound: one dependent FADD per step and thread.
-// BAND: fixed-capacity slots (see ras_small): the number of listed triangles is read from the device counter, the walk
+// ---- large triangles: Interpolate (:615-637), one thread per (triangle, edge, chain) -----------------
+// The four accumulation chains of an edge (x, zinv, pos3d.x, pos3d.y) are independent of each other, so each runs its
+// own serial loop -- 12 threads per triangle -- and writes its field of every sample.  A 2160-row edge is latency-bound:
+// one dependent FADD per step and thread.
+// BAND: fixed-capacity slots (see ras_setup): the number of listed triangles is read from the device counter, the walk
 // still runs over every step (the accumulation is serial) but only samples on rows of the band are stored, at y - y0.
 template <bool BAND>
 __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* listed large triangles (upper bound if BAND) */,
-                                 const RasCounters* __restrict__ ctr, EdgeSample* __restrict__ samples,
-                                 unsigned* __restrict__ rowOwner, int y0, int y1) {
+                                 const RasCounters* __restrict__ ctr, EdgeSample* __restrict__ samples, int y0, int y1) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gid / 15, rem = gid - 15 * i, e = rem / 5, ch = rem - 5 * e;
+    const int i = gid / 12, rem = gid - 12 * i, e = rem >> 2, ch = rem & 3;
     if (i >= (BAND ? (int)ctr->nBig : T)) return;
     const TriSetup s = ts[i];
-    if (!s.drawn) return;
-    if (!BAND && rem < 5)  // five threads share the owner table of this triangle's rows
-        for (int r = rem; r < s.rows; r += 5) rowOwner[s.rowBase + r] = (unsigned)i;
     const int j = (e + 1) % 3;  // :707
     const int n = abs(s.vy[e] - s.vy[j]) + 1;  // :712
     unsigned off = s.sampleBase;
@@ -385,17 +424,20 @@ __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* liste
         step = xdiv_step((float)(s.vx[j] - s.vx[e]), div);
     } else if (ch == 1) {
         cur = s.vz[e];
-        step = xdiv_step(xsub(s.vz[j], s.vz[e]), div);
+        step = xdiv_step(xsub(s.vz[j], cur), div);
+    } else if (ch == 2) {
+        cur = s.vpx[e];
+        step = xdiv_step(xsub(s.vpx[j], cur), div);
     } else {
-        cur = s.vp[3 * e + (ch - 2)];
-        step = xdiv_step(xsub(s.vp[3 * j + (ch - 2)], cur), div);
+        cur = s.vpy[e];
+        step = xdiv_step(xsub(s.vpy[j], cur), div);
     }
-    float* out = reinterpret_cast<float*>(samples + off) + ch;  // field ch of sample 0; samples are 5 words apart
+    float* out = reinterpret_cast<float*>(samples + off) + ch;  // field ch of sample 0; samples are 4 words apart
+    int kLo = 0, kHi = n - 1, stride = 4;
     if (BAND) {
         // step k lies on row vy[e] + sgn*k: the steps before the band only accumulate, the steps inside it are
         // stored, the steps after it are not needed by anyone
         const int ya = s.vy[e], sgn = (s.vy[j] > ya) - (s.vy[j] < ya);
-        int kLo, kHi;
         if (sgn > 0) {
             kLo = y0 - ya;
             kHi = y1 - 1 - ya;
@@ -409,242 +451,397 @@ __global__ void ras_edges_kernel(const TriSetup* __restrict__ ts, int T /* liste
         kLo = max(kLo, 0);
         kHi = min(kHi, n - 1);
         if (kLo > kHi) return;
-        for (int k = 0; k < kLo; ++k) cur = xadd(cur, step);  // :626-636 -- serial float accumulation, order matters
-        out += 5 * (ya + sgn * kLo - y0);
-        const int stride = 5 * sgn;
-        if (ch == 0) {
-            for (int k = kLo; k <= kHi; ++k, out += stride) {
-                *reinterpret_cast<int*>(out) = f2i_x86(cur);
-                cur = xadd(cur, step);
-            }
-        } else {
-            for (int k = kLo; k <= kHi; ++k, out += stride) {
-                *out = cur;
-                cur = xadd(cur, step);
-            }
-        }
-    } else if (ch == 0) {
-        for (int k = 0; k < n; ++k, out += 5) {  // :626-636 -- serial float accumulation, order matters
+        out += 4 * (ya + sgn * kLo - y0);
+        stride = 4 * sgn;
+    }
+    for (int k = 0; k < kLo; ++k) cur = xadd(cur, step);  // :626-636 -- serial float accumulation, order matters
+    if (ch == 0) {
+        for (int k = kLo; k <= kHi; ++k, out += stride) {
             *reinterpret_cast<int*>(out) = f2i_x86(cur);
             cur = xadd(cur, step);
         }
     } else {
-        for (int k = 0; k < n; ++k, out += 5) {
+        for (int k = kLo; k <= kHi; ++k, out += stride) {
             *out = cur;
             cur = xadd(cur, step);
         }
     }
 }
 
-// ---- stage 3: ComputePolygonRows' per-row resolve (:716-733) + DrawRows/DrawLineSDL/Bresenham ----
-// bandH > 0: band-slot layout, edge e's sample of row y sits at sampleBase + e*bandH + (y - y0)
-__device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSample* __restrict__ samples, int y,
-                                              int bandH = 0, int y0 = 0) {
-    RowRec r;
-    r.lx = INT_MAX;    // :696
-    r.rx = -INT_MAX;   // :697
-    r.lz = r.rz = 0.f;
-    r.lp[0] = r.lp[1] = r.lp[2] = r.rp[0] = r.rp[1] = r.rp[2] = 0.f;
-    r.pad[0] = r.pad[1] = 0;
-    unsigned off = s.sampleBase;
-    for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
-        const int j = (e + 1) % 3;
-        const int ya = s.vy[e], yb = s.vy[j];
-        const int n = abs(ya - yb) + 1;
-        if (y >= min(ya, yb) && y <= max(ya, yb)) {
-            const EdgeSample q = bandH > 0 ? samples[s.sampleBase + (unsigned)(e * bandH + (y - y0))]
-                                           : samples[off + (unsigned)abs(y - ya)];
-            if (q.x < r.lx) {  // :718 strict: the first edge to reach an extreme keeps its attributes
-                r.lx = q.x;
-                r.lz = q.zinv;
-                r.lp[0] = q.p[0]; r.lp[1] = q.p[1]; r.lp[2] = q.p[2];
-            }
-            if (q.x > r.rx) {  // :726
-                r.rx = q.x;
-                r.rz = q.zinv;
-                r.rp[0] = q.p[0]; r.rp[1] = q.p[1]; r.rp[2] = q.p[2];
-            }
-        }
-        off += (unsigned)n;
-    }
-    return r;
-}
-
-// fragments i in [i0,i1) of one row; Bresenham with dy == 0 (:639-672): x = lx+1+i, zinv = lz + zstep*float(i)
-__device__ __forceinline__ void raster_span(unsigned long long* __restrict__ keyRow, int lx, float lz, float zstep,
-                                            unsigned tri, int i0, int i1, int istride) {
-    for (int i = i0; i < i1; i += istride) {
-        const float zinv = xadd(lz, xmul(zstep, (float)i));  // :667
-        if (zinv > 0.0f)                                     // :606 against a buffer cleared to 0 (:188)
-            atomicMax(keyRow + (lx + 1 + i), pack_key(zinv, tri, 1u));
-    }
-}
-
-constexpr int kShortRow = 8;
-
-
-template <bool BAND>
-__global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restrict__ ts,
-                                                       const RasCounters* __restrict__ ctr,
-                                                       const EdgeSample* __restrict__ samples,
-                                                       const unsigned* __restrict__ rowOwner, unsigned nRows,
-                                                       RowRec* __restrict__ rows,
-                                                       unsigned long long* __restrict__ keys, int W, int y0,
-                                                       int y1, unsigned long long* __restrict__ stats) {
-    const unsigned rid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    int lx = 0, pixels = 0, i0 = 0, i1 = 0, y = 0;
-    float lz = 0.f, zstep = 0.f;
-    unsigned tri = 0;
-    const int bandH = y1 - y0;
-    // BAND: thread rid <-> (slot rid / bandH, row y0 + rid % bandH); otherwise the rows of the listed triangles are
-    // packed and rowOwner names the triangle
-    const unsigned slot = BAND ? rid / (unsigned)bandH : 0u;
-    if (BAND ? slot < ctr->nBig : rid < nRows) {
-        const TriSetup s = ts[BAND ? slot : rowOwner[rid]];
-        tri = (unsigned)s.tri;
-        y = BAND ? y0 + (int)(rid - slot * (unsigned)bandH) : s.minY + (int)(rid - s.rowBase);
-        // DrawRows (:743): rows with y outside the screen are skipped; outside the band: another GPU's
-        if (y >= y0 && y < y1 && y >= s.minY && y < s.minY + s.rows) {
-            RowRec r = BAND ? resolve_row(s, samples, y, bandH, y0) : resolve_row(s, samples, y);
-            rows[rid] = r;
-            lx = r.lx;
-            lz = r.lz;
-            pixels = r.rx - r.lx;                              // :598
-            i0 = max(0, -lx - 1);                              // :663 x >= 0
-            i1 = min(pixels, W - lx - 1);                      //      x <  W
-            if (i1 < i0) i1 = i0;
-            if (i1 > i0) zstep = xdiv_step(xsub(r.rz, r.lz), (float)pixels);  // :648
-        }
-    }
-    const int count = i1 - i0;
-    if (stats) {
-        unsigned long long c = (unsigned long long)count;
-        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if (lane == 0 && c) atomicAdd(stats + B2R_STAT_RAS_DEPTH_TESTS, c);
-    }
-    unsigned long long* keyRow = keys + (size_t)(y - y0) * (size_t)W;
-    // short rows: each lane walks its own; long rows: the whole warp walks them one at a time
-    const bool isLong = count > kShortRow;
-    if (count > 0 && !isLong) raster_span(keyRow, lx, lz, zstep, tri, i0, i1, 1);
-    unsigned longMask = __ballot_sync(0xffffffffu, isLong);
-    while (longMask) {
-        const int src = __ffs(longMask) - 1;
-        longMask &= longMask - 1;
-        const int blx = __shfl_sync(0xffffffffu, lx, src);
-        const float blz = __shfl_sync(0xffffffffu, lz, src);
-        const float bzs = __shfl_sync(0xffffffffu, zstep, src);
-        const unsigned btri = __shfl_sync(0xffffffffu, tri, src);
-        const int bi0 = __shfl_sync(0xffffffffu, i0, src), bi1 = __shfl_sync(0xffffffffu, i1, src);
-        const int by = __shfl_sync(0xffffffffu, y, src);
-        raster_span(keys + (size_t)(by - y0) * (size_t)W, blx, blz, bzs, btri, bi0 + lane, bi1, 32);
-    }
-}
-
-// ---- stage 4: PixelShader (:549-589) for the depth winner of every pixel ------------------------
-// Loads of one pixel's winner: its row ends and the triangle's normal/colour.
-struct ShadeIn {
-    RowRec r;
-    V3 normal, color;
+// ---- the tile kernel ----------------------------------------------------------------------------------
+struct TileArgs {
+    const unsigned* tileOffset;  // nTiles + 1
+    const unsigned* refs;        // tile lists: triangle index, or kBigRef | large-triangle slot
+    unsigned* tileCount;         // re-armed (zeroed) for the next frame
+    const TriSetup* bigTs;
+    const EdgeSample* samples;   // edge samples of the large triangles
+    RasCounters* ctr;
+    const unsigned* tileMslot;   // first partial-result slot of a tile drawn by several jobs
+    const uint2* jobTile;        // job -> (tile, slice of its list)
+    unsigned* tileDone;          // jobs of the tile that have delivered their partial result
+    uint4* partials;             // per slot, per pixel: (zinv bits, triangle, pos3d.x, pos3d.y)
+    int tilesX, nTiles;
+    int nEpochs;                 // ceil(T / 2^20), see the depth key below
 };
-__device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long long key, int y,
-                                               const TriSetup* __restrict__ bigTs, const int2* __restrict__ triInfo,
-                                               const SmallRow* __restrict__ rowRec, const RowRec* __restrict__ rows) {
-    ShadeIn in;
-    const unsigned tri = key_triangle(key);
-    const float* t = reinterpret_cast<const float*>(a.raw + (size_t)tri * a.stride);
-    if (key & 1ull) {
-        const int2 info = triInfo[tri];  // (slot in the large-triangle list, minY)
-        in.r = rows[bigTs[info.x].rowBase + (unsigned)(y - info.y)];
-    } else {
-        const float4* q = reinterpret_cast<const float4*>(rowRec + small_row_slot(tri, y));
-        const float4 q0 = q[0], q1 = q[1];
-        in.r.lx = __float_as_int(q0.x);
-        in.r.rx = __float_as_int(q0.y);
-        in.r.lz = q0.z;
-        in.r.rz = q0.w;
-        in.r.lp[0] = q1.x; in.r.lp[1] = q1.y; in.r.lp[2] = 1.0f;
-        in.r.rp[0] = q1.z; in.r.rp[1] = q1.w; in.r.rp[2] = 1.0f;
-        in.r.pad[0] = in.r.pad[1] = 0;
+
+// Depth key of a pixel, one 64-bit word in shared memory updated with atomicMax:
+//   high word  zinv bits (zinv > 0, so unsigned order == float order): larger zinv wins (:606)
+//   low word   (0xFFFFF - (triangle & 0xFFFFF)) << 12 | row item: among equal zinv the LOWER triangle index wins -- the
+//              reference's strict `>` in draw order -- and the low 12 bits name the row item (this round's thread)
+//              whose span produced the fragment, so that the pixel can fetch its attributes right after the round.
+// The triangle field holds 20 bits.  Scenes of more than 2^20 triangles are drawn in epochs of 2^20 consecutive
+// indices, lowest first (every epoch walks the tile's list and skips the other epochs' triangles); between epochs
+// the low word of every covered pixel is raised to 0xFFFFFFFF, so a later epoch (higher indices) can only take a
+// pixel with a strictly larger zinv.  Within a tile a triangle appears in exactly one round of one epoch and has at
+// most one fragment per pixel, so a pixel's low word changes whenever its owner does.
+constexpr int kTriBits = 20, kSlotBits = 12;
+constexpr unsigned kTriMask = (1u << kTriBits) - 1u;
+
+struct RowRec {  // what PixelShader needs from the winning row: Bresenham's pos3d.xy start and step (:649, :668)
+    int lx;
+    float lpx, psx, lpy, psy;
+    unsigned tri;
+    int pad[2];
+};
+
+constexpr int kPixPerThread = kTilePix / kTileThreads;  // 4: pixel p = tid + 256 i, a warp covers one tile row
+
+struct __align__(16) TileShared {
+    float4 samples[3 * kTileThreads];  // W -> A3: (int x, zinv, pos3d.x, pos3d.y) of row item r, edge e at [3r + e]
+    unsigned long long key[kTilePix];  // depth keys, 0 = nothing drawn (depthBuffer = 0, :188)
+    RowRec rec[kTileThreads];          // A3 -> G: the round's row items
+    // the triangles of the current batch, one per thread (VertexShader output)
+    int vy[3][kTileThreads], vx[3][kTileThreads];
+    float vz[3][kTileThreads], vpx[3][kTileThreads], vpy[3][kTileThreads];
+    unsigned tri[kTileThreads];    // index in the caller's array
+    unsigned sbase[kTileThreads];  // large triangle: where its edge samples start; kSmallTri otherwise
+    int yA[kTileThreads];          // first row inside the tile
+    unsigned rowBase[kTileThreads + 4];  // exclusive prefix sum of the rows inside the tile
+    unsigned short rowTri[kTileThreads]; // row item of the current round -> triangle slot of the batch
+    unsigned warpSums[8];
+};
+static_assert(sizeof(TileShared) <= 48 * 1024, "ras_tile uses static shared memory");
+
+__global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, TileArgs g) {
+    __shared__ TileShared S;
+    __shared__ bool lastJob;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (blockIdx.x >= g.tileOffset[g.nTiles + 1]) return;  // the grid is sized for the worst case
+    const uint2 job = g.jobTile[blockIdx.x];
+    const int tile = (int)job.x, slice = (int)job.y;
+    const int tileX = tile % g.tilesX, tileY = tile / g.tilesX;
+    const int X0 = tileX << kTileShift, X1 = min(X0 + kTileW, a.W);
+    const int Y0 = a.y0 + (tileY << kTileShift), Y1 = min(Y0 + kTileH, a.y1);
+    const unsigned listLen = g.tileOffset[tile + 1] - g.tileOffset[tile];
+    const unsigned beg = g.tileOffset[tile] + (unsigned)slice * kSlice, nRefs = min((unsigned)kSlice, listLen - (unsigned)slice * kSlice);
+    const unsigned nJobs = max(1u, (listLen + kSlice - 1) / kSlice);
+    // last kernel of the frame: leave the per-frame counters and the tile counts clear for the next one
+    if (tid == 0 && slice == 0) {
+        g.tileCount[tile] = 0u;
+        if (tile == 0) g.ctr->nBig = g.ctr->bigRows = g.ctr->bigSamples = g.ctr->err = g.ctr->totalRefs = g.ctr->blocksDone = g.ctr->totalJobs = 0u;
     }
-    if (a.stride == 64) {  // the rasteriser's own 64-byte Triangle: records are 16-byte aligned, two 128-bit loads
-        const float4 n4 = reinterpret_cast<const float4*>(t)[2], c4 = reinterpret_cast<const float4*>(t)[3];
-        in.normal = mk3(n4.y, n4.z, n4.w);
-        in.color = mk3(c4.x, c4.y, c4.z);
-    } else {
-        in.normal = mk3(t[9], t[10], t[11]);
-        in.color = mk3(t[12], t[13], t[14]);
-    }
-    return in;
-}
-
-// PixelShader (:549-589) for the fragment of pixel x on the winner's row.
-__device__ __forceinline__ void shade_pixel(const RasFrame& fr, const ShadeIn& in, int x, float& depth,
-                                            float& focal, V3& colour) {
-    const RowRec& r = in.r;
-    const int pixels = r.rx - r.lx;
-    const float fi = (float)(x - r.lx - 1);
-    const float fdx = (float)pixels;
-    const float zinv = xadd(r.lz, xmul(xdiv_step(xsub(r.rz, r.lz), fdx), fi));               // :648,667
-    const V3 lp = mk3(r.lp[0], r.lp[1], r.lp[2]), rp = mk3(r.rp[0], r.rp[1], r.rp[2]);
-    const V3 dp = xsub3(rp, lp);  // the z difference is exactly 0 (pos3d.z == 1): xdiv_step avoids the division slow path
-    const V3 pos3d = xadd3(lp, xscale3(mk3(xdiv_step(dp.x, fdx), xdiv_step(dp.y, fdx), xdiv_step(dp.z, fdx)), fi));  // :649,668
-    depth = zinv;  // == the key's high word
-    pixel_shader_core(fr, zinv, pos3d, in.normal, in.color, focal, colour);
-}
-
-// kShadePixels pixels per thread (256 apart in x, so every access stays coalesced): the key loads of all of them
-// are issued first, then all row-record / triangle loads, then the arithmetic -- the kernel is bound by the
-// latency of that dependent load chain, not by bandwidth.
-constexpr int kShadePixels = 2;
-
-__global__ void __launch_bounds__(256, 5) ras_shade_kernel(RasLaunch a, const TriSetup* __restrict__ bigTs,
-                                                        const int2* __restrict__ triInfo,
-                                                        const SmallRow* __restrict__ rowRec,
-                                                        const RowRec* __restrict__ rows,
-                                                        unsigned long long* __restrict__ keys,
-                                                        RasCounters* __restrict__ ctr) {
-    // last kernel of the frame: leave the per-frame counters clear for the next one (no memset in steady state)
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) ctr->nBig = ctr->bigRows = ctr->bigSamples = ctr->err = 0u;
-    const int y = a.y0 + blockIdx.y;
-    const int xbase = blockIdx.x * (256 * kShadePixels) + threadIdx.x;
-    unsigned long long key[kShadePixels];
+    unsigned long long nTests = 0;
+    // the winner of this thread's pixels so far: low key word seen last, triangle, interpolated pos3d.xy
+    unsigned seenLo[kPixPerThread], wtri[kPixPerThread];
+    float posx[kPixPerThread], posy[kPixPerThread];
 #pragma unroll
-    for (int p = 0; p < kShadePixels; ++p) {
-        const int x = xbase + 256 * p;
-        key[p] = (x < a.W) ? keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x] : 0ull;
+    for (int i = 0; i < kPixPerThread; ++i) {
+        seenLo[i] = 0u;
+        wtri[i] = 0u;
+        posx[i] = posy[i] = 0.f;
     }
-    ShadeIn in[kShadePixels];
+    if (nRefs != 0u) {
 #pragma unroll
-    for (int p = 0; p < kShadePixels; ++p) {
-        const int x = xbase + 256 * p;
-        if (key[p] != 0ull) {
-            keys[(size_t)(y - a.y0) * (size_t)a.W + (size_t)x] = 0ull;  // depthBuffer = 0 (:188) for the next frame
-            in[p] = shade_fetch(a, key[p], y, bigTs, triInfo, rowRec, rows);
+        for (int i = 0; i < kPixPerThread; ++i) S.key[tid + kTileThreads * i] = 0ull;
+    }
+    const int bandH = a.y1 - a.y0;
+    const int nEpochs = nRefs ? g.nEpochs : 0;
+    for (int epoch = 0; epoch < nEpochs; ++epoch) {
+        for (unsigned b0 = 0; b0 < nRefs; b0 += kTileThreads) {
+            const int nb = (int)min((unsigned)kTileThreads, nRefs - b0);
+            // ---- A1: one listed triangle per thread ----
+            unsigned cnt = 0;
+            if (tid < nb) {
+                const unsigned ref = g.refs[beg + b0 + tid];
+                int minY = 0, maxY = -1;
+                if (ref & kBigRef) {
+                    const TriSetup* s = g.bigTs + (ref & ~kBigRef);
+                    if (((unsigned)s->tri >> kTriBits) == (unsigned)epoch) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            S.vx[k][tid] = s->vx[k];
+                            S.vy[k][tid] = s->vy[k];
+                            S.vz[k][tid] = s->vz[k];
+                            S.vpx[k][tid] = s->vpx[k];
+                            S.vpy[k][tid] = s->vpy[k];
+                        }
+                        minY = s->minY;
+                        maxY = minY + s->rows - 1;
+                        S.tri[tid] = (unsigned)s->tri;
+                        S.sbase[tid] = s->sampleBase;
+                    }
+                } else if ((ref >> kTriBits) == (unsigned)epoch) {
+                    float t[12];
+                    load_vertices(a, (int)ref, t);
+                    minY = INT_MAX;
+                    maxY = INT_MIN;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const RPixel v = vertex_shader<true>(a.fr, mk3(t[3 * k], t[3 * k + 1], t[3 * k + 2]));  // :760-761
+                        S.vx[k][tid] = v.x;
+                        S.vy[k][tid] = v.y;
+                        S.vz[k][tid] = v.zinv;
+                        S.vpx[k][tid] = v.p.x;
+                        S.vpy[k][tid] = v.p.y;
+                        minY = min(minY, v.y);
+                        maxY = max(maxY, v.y);
+                    }
+                    S.tri[tid] = ref;
+                    S.sbase[tid] = kSmallTri;
+                }
+                const int ya = max(minY, Y0), yb = min(maxY, Y1 - 1);  // DrawRows :743, the band, the tile
+                S.yA[tid] = ya;
+                cnt = (unsigned)max(yb - ya + 1, 0);
+            }
+            {   // block-wide exclusive prefix sum of cnt -> rowBase[0..256]
+                unsigned inc = cnt;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned x = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc += x;
+                }
+                if (lane == 31) S.warpSums[warp] = inc;
+                __syncthreads();
+                unsigned wbase = 0;
+#pragma unroll
+                for (int k = 0; k < kTileThreads / 32; ++k)
+                    if (k < warp) wbase += S.warpSums[k];
+                S.rowBase[tid] = wbase + inc - cnt;
+                if (tid == kTileThreads - 1) S.rowBase[kTileThreads] = wbase + inc;
+                __syncthreads();
+            }
+            // ---- rounds of whole triangles with at most 256 row items between them ----
+            int ja = 0;
+            while (ja < nb) {
+                const unsigned base = S.rowBase[ja];
+                const bool fits = tid >= ja && tid < nb && S.rowBase[tid + 1] - base <= (unsigned)kTileThreads;
+                const int nt = __syncthreads_count(fits);  // >= 1: one triangle has at most kTileH rows in the tile
+                const int jb = ja + nt;
+                const int nrows = (int)(S.rowBase[jb] - base);
+                if (nrows == 0) {  // (uniform) nothing of these triangles lies on the tile's rows
+                    ja = jb;
+                    continue;
+                }
+                if (fits) {
+                    const int r0 = (int)(S.rowBase[tid] - base), r1 = (int)(S.rowBase[tid + 1] - base);
+                    for (int r = r0; r < r1; ++r) S.rowTri[r] = (unsigned short)tid;
+                }
+                // ---- W: Interpolate (:615-637) of the small triangles' edges, one (triangle, edge) per thread ----
+                for (int t = tid; t < 3 * nt; t += kTileThreads) {
+                    const int jr = t / 3, e = t - 3 * jr, j = ja + jr, e2 = (e == 2) ? 0 : e + 1;  // :707
+                    if (S.sbase[j] != kSmallTri) continue;
+                    const int rj = (int)(S.rowBase[j] - base), cj = (int)(S.rowBase[j + 1] - base) - rj;
+                    if (cj == 0) continue;
+                    const int yLo = S.yA[j], yHi = yLo + cj - 1;
+                    const int ya = S.vy[e][j], yb = S.vy[e2][j];
+                    const int n = abs(ya - yb) + 1, sgn = (yb > ya) - (yb < ya);  // :712
+                    // step k lies on row ya + sgn*k: the steps before the tile's rows only accumulate, the steps
+                    // inside are stored, the steps after them are not needed by anyone
+                    int kLo, kHi;
+                    if (sgn > 0) {
+                        kLo = yLo - ya;
+                        kHi = yHi - ya;
+                    } else if (sgn < 0) {
+                        kLo = ya - yHi;
+                        kHi = ya - yLo;
+                    } else {
+                        kLo = (ya >= yLo && ya <= yHi) ? 0 : 1;
+                        kHi = 0;
+                    }
+                    kLo = max(kLo, 0);
+                    kHi = min(kHi, n - 1);
+                    if (kLo > kHi) continue;
+                    const Recip div = recip_make((float)max(n - 1, 1));  // :622
+                    const int ax = S.vx[e][j];
+                    float cx = (float)ax, cz = S.vz[e][j], cpx = S.vpx[e][j], cpy = S.vpy[e][j];  // fPixel(Pixel&)
+                    const float sx = xdiv_step_by((float)(S.vx[e2][j] - ax), div);  // Pixel operator- / fPixel operator/
+                    const float sz = xdiv_step_by(xsub(S.vz[e2][j], cz), div);
+                    const float spx = xdiv_step_by(xsub(S.vpx[e2][j], cpx), div);
+                    const float spy = xdiv_step_by(xsub(S.vpy[e2][j], cpy), div);
+                    for (int k = 0; k < kLo; ++k) {  // :626-636, serial accumulation
+                        cx = xadd(cx, sx);
+                        cz = xadd(cz, sz);
+                        cpx = xadd(cpx, spx);
+                        cpy = xadd(cpy, spy);
+                    }
+                    int idx = 3 * (rj + (ya + sgn * kLo - yLo)) + e;
+                    const int stride = 3 * sgn;
+                    for (int k = kLo; k <= kHi; ++k, idx += stride) {
+                        // int(current.x): the chain stays within coord_margin of the vertex range, which passed the
+                        // +-2^24 limit, so the plain truncating conversion equals the x86 one
+                        S.samples[idx] = make_float4(__int_as_float(__float2int_rz(cx)), cz, cpx, cpy);
+                        cx = xadd(cx, sx);
+                        cz = xadd(cz, sz);
+                        cpx = xadd(cpx, spx);
+                        cpy = xadd(cpy, spy);
+                    }
+                }
+                __syncthreads();
+                // ---- A3: ComputePolygonRows' resolve (:705-733) + DrawRows / DrawLineSDL / Bresenham (dy == 0) ----
+                if (tid < nrows) {
+                    const int j = S.rowTri[tid];
+                    const int y = S.yA[j] + tid - (int)(S.rowBase[j] - base);
+                    const unsigned sb = S.sbase[j];
+                    int lx = INT_MAX, rx = -INT_MAX;  // :696-697
+                    float lz = 0.f, rz = 0.f, lpx = 0.f, lpy = 0.f, rpx = 0.f, rpy = 0.f;
+                    unsigned off = sb;
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {  // edges 0->1, 1->2, 2->0 in order; strict </> so the first edge to
+                        const int e2 = (e == 2) ? 0 : e + 1;  // reach an extreme x keeps its attributes (:718, :726)
+                        const int ya = S.vy[e][j], yb = S.vy[e2][j];
+                        if (y >= min(ya, yb) && y <= max(ya, yb)) {
+                            float4 q;
+                            if (sb == kSmallTri) {
+                                q = S.samples[3 * tid + e];
+                            } else {
+                                const unsigned at = a.bandSlots ? sb + (unsigned)(e * bandH + (y - a.y0)) : off + (unsigned)abs(y - ya);
+                                q = *reinterpret_cast<const float4*>(g.samples + at);
+                            }
+                            const int x = __float_as_int(q.x);
+                            if (x < lx) {
+                                lx = x; lz = q.y; lpx = q.z; lpy = q.w;
+                            }
+                            if (x > rx) {
+                                rx = x; rz = q.y; rpx = q.z; rpy = q.w;
+                            }
+                        }
+                        off += (unsigned)(abs(ya - yb) + 1);
+                    }
+                    const int pixels = rx - lx;                                         // :598
+                    const int i0 = max(0, X0 - lx - 1), i1 = min(pixels, X1 - lx - 1);  // :663 keeps 0 <= x < W; here: the tile's columns
+                    if (i1 > i0) {
+                        const Recip fdx = recip_make((float)pixels);
+                        const float zstep = xdiv_step_by(xsub(rz, lz), fdx);  // :648 (constant-depth rows: 0/n)
+                        RowRec r;
+                        r.lx = lx;
+                        r.lpx = lpx;
+                        r.lpy = lpy;
+                        r.psx = xdiv_step_by(xsub(rpx, lpx), fdx);            // :649
+                        r.psy = xdiv_step_by(xsub(rpy, lpy), fdx);
+                        r.tri = S.tri[j];
+                        r.pad[0] = r.pad[1] = 0;
+                        S.rec[tid] = r;
+                        const unsigned lo = ((kTriMask - (r.tri & kTriMask)) << kSlotBits) | (unsigned)tid;
+                        unsigned long long* krow = S.key + ((y - Y0) * kTileW - X0 + lx + 1);  // pixel of fragment q: krow[q]
+                        for (int q = i0; q < i1; ++q) {
+                            const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
+                            if (zinv > 0.0f)                                     // :606 against a buffer cleared to 0 (:188)
+                                atomicMax(krow + q, ((unsigned long long)__float_as_uint(zinv) << 32) | lo);
+                        }
+                        nTests += (unsigned long long)(i1 - i0);
+                    }
+                }
+                __syncthreads();
+                // ---- G: every pixel whose owner changed in this round fetches the owner's row (:667-668) ----
+#pragma unroll
+                for (int i = 0; i < kPixPerThread; ++i) {
+                    const unsigned lo = (unsigned)S.key[tid + kTileThreads * i];
+                    if (lo != seenLo[i]) {
+                        seenLo[i] = lo;
+                        const RowRec* r = &S.rec[lo & ((1u << kSlotBits) - 1u)];
+                        const float fi = (float)(X0 + lane - r->lx - 1);
+                        posx[i] = xadd(r->lpx, xmul(r->psx, fi));
+                        posy[i] = xadd(r->lpy, xmul(r->psy, fi));
+                        wtri[i] = r->tri;
+                    }
+                }
+                // no barrier here: the next round's first writes to anything read above come after its own barriers
+                ja = jb;
+            }
+            __syncthreads();
+        }
+        if (epoch + 1 < nEpochs) {  // freeze: later epochs hold higher triangle indices and lose every tie
+#pragma unroll
+            for (int i = 0; i < kPixPerThread; ++i) {
+                unsigned long long* k = &S.key[tid + kTileThreads * i];
+                if (*k != 0ull) {
+                    *k |= 0xFFFFFFFFull;
+                    seenLo[i] = 0xFFFFFFFFu;
+                }
+            }
+            __syncthreads();
         }
     }
+    if (a.stats) {
+        for (int off = 16; off > 0; off >>= 1) nTests += __shfl_xor_sync(0xffffffffu, nTests, off);
+        if (lane == 0 && nTests) atomicAdd(a.stats + B2R_STAT_RAS_DEPTH_TESTS, nTests);
+    }
+    unsigned wbits[kPixPerThread];
 #pragma unroll
-    for (int p = 0; p < kShadePixels; ++p) {
-        const int x = xbase + 256 * p;
-        if (x >= a.W) continue;
-        float depth = 0.f, focal = 0.f;
-        V3 colour = mk3(0.f, 0.f, 0.f);
-        int winner = -1;
-        if (key[p] != 0ull) {
-            winner = (int)key_triangle(key[p]);
-            shade_pixel(a.fr, in[p], x, depth, focal, colour);
+    for (int i = 0; i < kPixPerThread; ++i) wbits[i] = nRefs ? (unsigned)(S.key[tid + kTileThreads * i] >> 32) : 0u;
+    if (nJobs > 1u) {
+        // The tile's list was split: every job leaves its per-pixel winners in its slot; the last one to arrive merges
+        // them -- larger zinv first, lower triangle index among equals (:606) -- and shades.
+        uint4* mine = g.partials + ((size_t)g.tileMslot[tile] + (size_t)slice) * kTilePix;
+#pragma unroll
+        for (int i = 0; i < kPixPerThread; ++i)
+            mine[tid + kTileThreads * i] = make_uint4(wbits[i], wtri[i], __float_as_uint(posx[i]), __float_as_uint(posy[i]));
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            lastJob = atomicAdd(&g.tileDone[tile], 1u) == nJobs - 1u;
+            if (lastJob) g.tileDone[tile] = 0u;  // re-armed for the next frame
         }
-        const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;
-        if (a.depth) a.depth[idx] = depth;
-        if (a.colours) {
-            a.colours[3 * idx] = colour.x;
-            a.colours[3 * idx + 1] = colour.y;
-            a.colours[3 * idx + 2] = colour.z;
+        __syncthreads();
+        if (!lastJob) return;
+        __threadfence();
+        const uint4* all = g.partials + (size_t)g.tileMslot[tile] * kTilePix;
+        for (unsigned sl = 0; sl < nJobs; ++sl) {
+            if (sl == (unsigned)slice) continue;
+#pragma unroll
+            for (int i = 0; i < kPixPerThread; ++i) {
+                const uint4 o = __ldcg(&all[(size_t)sl * kTilePix + tid + kTileThreads * i]);
+                if (o.x > wbits[i] || (o.x == wbits[i] && o.x != 0u && o.y < wtri[i])) {
+                    wbits[i] = o.x;
+                    wtri[i] = o.y;
+                    posx[i] = __uint_as_float(o.z);
+                    posy[i] = __uint_as_float(o.w);
+                }
+            }
         }
-        if (a.focal) a.focal[idx] = focal;
-        if (a.winner) a.winner[idx] = winner;
-        // CalculateDOF without depth of field + PutPixelSDL (:516-526), fused
-        if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(colour.x, colour.y, colour.z) : 0u;
+    }
+    // ---- C: PixelShader (:549-589) for the depth winner of every pixel, CalculateDOF/PutPixelSDL fused ----
+    const int x = X0 + lane;
+    if (x < X1) {
+#pragma unroll
+        for (int i = 0; i < kPixPerThread; ++i) {
+            const int y = Y0 + warp + (kTileThreads / 32) * i;
+            if (y >= Y1) break;
+            float depth = 0.f, focal = 0.f;
+            V3 colour = mk3(0.f, 0.f, 0.f);
+            int winner = -1;
+            const unsigned bits = wbits[i];
+            if (bits != 0u) {
+                winner = (int)wtri[i];
+                depth = __uint_as_float(bits);
+                const float4* t = reinterpret_cast<const float4*>(a.raw + (size_t)wtri[i] * 64);
+                const float4 n4 = t[2], c4 = t[3];  // (v2.z, normal), (colour, isCulled)
+                const V3 normal = mk3(n4.y, n4.z, n4.w), color = mk3(c4.x, c4.y, c4.z);
+                pixel_shader_core<true>(a.fr, depth, mk3(posx[i], posy[i], 1.0f), normal, color, focal, colour);
+            }
+            const unsigned idx = (unsigned)y * (unsigned)a.W + (unsigned)x;  // W, H <= 32768
+            if (a.depth) a.depth[idx] = depth;
+            if (a.colours) {
+                float* c3 = a.colours + (size_t)idx * 3;
+                c3[0] = colour.x;
+                c3[1] = colour.y;
+                c3[2] = colour.z;
+            }
+            if (a.focal) a.focal[idx] = focal;
+            if (a.winner) a.winner[idx] = winner;
+            // CalculateDOF without depth of field + PutPixelSDL (:516-526), fused
+            if (a.surface) a.surface[idx] = inside_border(x, y, a.W, a.H) ? pack_xrgb(colour.x, colour.y, colour.z) : 0u;
+        }
     }
 }
 
@@ -683,6 +880,28 @@ __global__ void ras_cull_kernel(const unsigned char* __restrict__ raw, int strid
     culled[i] = (unsigned char)cull;
 }
 
+// ---- 60-byte scenes (the raytracer's Triangle) as 64-byte records, once per b2r_set_triangles ------------
+__global__ void ras_repack_kernel(const unsigned char* __restrict__ raw, int stride, int T, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T) return;
+    const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) v[k] = r[k];
+    v[15] = 0.f;  // isCulled lives in its own array (b2r_ras_cull / b2r_set_culled)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[(size_t)i * 4 + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+
+cudaError_t launch_ras_repack(Ctx* c, cudaStream_t s) {
+    if (c->stride == 64 || c->T == 0) return cudaSuccess;
+    cudaError_t e = c->raw64.reserve((size_t)c->T * 64);
+    if (e != cudaSuccess) return e;
+    ras_repack_kernel<<<(c->T + 255) / 256, 256, 0, s>>>(c->raw.as<unsigned char>(), c->stride, c->T, c->raw64.as<float4>());
+    c->launches++;
+    return cudaGetLastError();
+}
+
 // ---- host side ------------------------------------------------------------------
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -710,23 +929,25 @@ cudaError_t launch_ras_cull(Ctx* c, unsigned char* d_culled, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- host side ------------------------------------------------------------------
 // Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
-
-// Returns cudaErrorInvalidValue when a triangle exceeds the row/coordinate limits (-> B2R_E_CAPACITY).
-// Scenes of few triangles (T * band height row slots within this budget: ~100 MB of row records, ~200 MB of edge
-// samples) take the large-triangle path with fixed-capacity slots: nothing is read back, the frame is a plain
-// sequence of launches.  Larger scenes size the buffers from counters read back after the first kernel.
-constexpr size_t kBandSlotLimit = 2u << 20;
+// Scenes of few triangles (T * band height within this budget) give every large triangle a fixed-capacity slot of edge
+// samples and size the tile lists for the worst case: nothing is read back, the frame is a plain sequence of launches.
+// Larger scenes size both from counters read back after the first two kernels -- once per (scene, culling flags, frame
+// params, band): the counts are a pure function of those, so later frames of the same state run without the readback.
+constexpr size_t kBandSlotLimit = 2u << 20;  // edge-sample slots (T * band height)
+constexpr size_t kBandRefLimit = 1u << 20;   // tile-list entries (T * tiles)
 
 cudaError_t ras_take_error(Ctx* c) {
     if (!c->rasErrPending) return cudaSuccess;
     c->rasErrPending = false;
     RasCounters* ctr = c->rasScratch.as<RasCounters>();
-    unsigned flag = 0;
-    cudaError_t e = cudaMemcpy(&flag, &ctr->sticky, sizeof flag, cudaMemcpyDeviceToHost);
+    unsigned* flag = reinterpret_cast<unsigned*>(c->pinned);
+    cudaError_t e = cudaMemcpyAsync(flag, &ctr->sticky, sizeof *flag, cudaMemcpyDeviceToHost, c->stream);
     if (e != cudaSuccess) return e;
-    if (!flag) return cudaSuccess;
-    e = cudaMemset(&ctr->sticky, 0, sizeof flag);
+    if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+    if (!*flag) return cudaSuccess;
+    e = cudaMemsetAsync(&ctr->sticky, 0, sizeof *flag, c->stream);
     return e != cudaSuccess ? e : cudaErrorInvalidValue;
 }
 
@@ -734,115 +955,147 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     RasLaunch a = a0;
     const int T = a.T;
     const int bandH = a.y1 - a.y0;
+    const int tilesX = (a.W + kTileW - 1) >> kTileShift, tilesY = (bandH + kTileH - 1) >> kTileShift, nTiles = tilesX * tilesY;
     cudaError_t e;
-    // scratch: [counters 64 B][bigCounts uint2 x T][excl uint2 x T][blockSums][totals]; triInfo int2 x T separately
+    // scratch: [counters 256 B][tileCount][tileOffset][tileMslot][tileDone][bigCounts uint2 x T][excl uint2 x T][blockSums][totals]
     const int nbMax = (T + kScanBlock - 1) / kScanBlock + 1;
-    const size_t offCtr = 0, offCounts = 256, offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
+    const size_t offCtr = 0, offTileCount = 256, offTileOffset = align_up(offTileCount + sizeof(unsigned) * (size_t)nTiles, 256),
+                 offMslot = align_up(offTileOffset + sizeof(unsigned) * (size_t)(nTiles + 2), 256),
+                 offDone = align_up(offMslot + sizeof(unsigned) * (size_t)nTiles, 256),
+                 offCounts = align_up(offDone + sizeof(unsigned) * (size_t)nTiles, 256),
+                 offExcl = align_up(offCounts + sizeof(uint2) * (size_t)T, 256),
                  offSums = align_up(offExcl + sizeof(uint2) * (size_t)T, 256),
                  offTotals = align_up(offSums + sizeof(uint2) * (size_t)nbMax, 256), scratchBytes = offTotals + 256;
     const void* scratchBefore = c->rasScratch.p;
     if ((e = c->rasScratch.reserve(scratchBytes)) != cudaSuccess) return e;
-    if (c->rasScratch.p != scratchBefore &&  // fresh memory: the sticky error flag starts clear
-        (e = cudaMemsetAsync(c->rasScratch.p, 0, 256, s)) != cudaSuccess)
-        return e;
-    if ((e = c->rasTri.reserve(sizeof(TriSetup) * (size_t)(T + 1) + sizeof(int2) * (size_t)(T + 1) + 1024)) != cudaSuccess) return e;
-    if ((e = c->rasSmall.reserve(sizeof(SmallRow) * (size_t)kSmallRows * (size_t)(T + 1))) != cudaSuccess) return e;
-    if ((e = c->rasKeys.reserve(sizeof(unsigned long long) * (size_t)bandH * a.W + 256)) != cudaSuccess) return e;
     unsigned char* sc = c->rasScratch.as<unsigned char>();
+    if (c->rasScratch.p != scratchBefore) {  // fresh memory: the sticky error flag starts clear
+        if ((e = cudaMemsetAsync(sc, 0, 256, s)) != cudaSuccess) return e;
+        c->rasCtrDirty = true;
+    }
+    if ((e = c->rasTri.reserve(sizeof(unsigned) * (size_t)(T + 1) + 256 + sizeof(TriSetup) * (size_t)(T + 1))) != cudaSuccess) return e;
     RasCounters* ctr = reinterpret_cast<RasCounters*>(sc + offCtr);
+    unsigned* tileCount = reinterpret_cast<unsigned*>(sc + offTileCount);
+    unsigned* tileOffset = reinterpret_cast<unsigned*>(sc + offTileOffset);
+    unsigned* tileMslot = reinterpret_cast<unsigned*>(sc + offMslot);
+    unsigned* tileDone = reinterpret_cast<unsigned*>(sc + offDone);
     uint2* counts = reinterpret_cast<uint2*>(sc + offCounts);
     uint2* excl = reinterpret_cast<uint2*>(sc + offExcl);
     uint2* sums = reinterpret_cast<uint2*>(sc + offSums);
     uint2* totals = reinterpret_cast<uint2*>(sc + offTotals);
-    int2* triInfo = c->rasTri.as<int2>();
-    SmallRow* rowRec = c->rasSmall.as<SmallRow>();
-    TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(int2) * (size_t)(T + 1), 256));
-    unsigned long long* keys = c->rasKeys.as<unsigned long long>();
+    unsigned* triWord = c->rasTri.as<unsigned>();
+    TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(unsigned) * (size_t)(T + 1), 256));
 
-    const bool bandSlots = T > 0 && (size_t)T * (size_t)bandH <= kBandSlotLimit && c->optRasVariant != 1;
+    const bool bandSlots = (size_t)T * (size_t)bandH <= kBandSlotLimit && (size_t)T * (size_t)nTiles <= kBandRefLimit &&
+                           c->optRasVariant != 1;
     a.bandSlots = bandSlots ? 1 : 0;
-    // the sticky flag (second half of the struct) survives until the host has reported it
-    // ... and so do the per-frame counters, cleared by the previous frame's shade kernel; clear them here only
-    // after a draw that did not get that far (or on a fresh buffer, above)
-    if (c->rasCtrDirty && (e = cudaMemsetAsync(ctr, 0, offsetof(RasCounters, sticky), s)) != cudaSuccess) return e;
-    c->rasCtrDirty = true;
-    // depthBuffer = 0 (:188): the shade pass of the previous frame leaves the key buffer cleared; clear it here
-    // only when the buffer is new or was last used for a different band size
-    const size_t keyBytes = sizeof(unsigned long long) * (size_t)bandH * a.W;
-    if (c->rasKeysClean != keyBytes || c->rasKeysCleanPtr != (void*)keys) {
-        if ((e = cudaMemsetAsync(keys, 0, keyBytes, s)) != cudaSuccess) return e;
+    // the per-frame counters and the tile counts are left clear by the previous frame's tile kernel; clear them here
+    // only after a draw that did not get that far, on a fresh buffer, or when the tile grid changed shape
+    // (the sticky flag, second half of the counter block, survives until the host has reported it)
+    if (c->rasCtrDirty || c->rasTilesClean != (size_t)nTiles) {
+        if ((e = cudaMemsetAsync(ctr, 0, offsetof(RasCounters, sticky), s)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(tileCount, 0, offTileOffset - offTileCount, s)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(tileDone, 0, offCounts - offDone, s)) != cudaSuccess) return e;
     }
-    c->rasKeysClean = 0;
-    RasCounters host{};
-    const RowRec* rowsPtr = nullptr;
+    c->rasCtrDirty = true;
+
+    // job table of ras_tile: a tile whose list is longer than kSlice is split over ceil(len / kSlice) CTAs
+    unsigned nBig = 0, nSamples = 0;
+    size_t refCap, sampleCap;
+    Ctx::RasSizes& z = c->rasSizes;
+    const bool sized = z.valid && z.gen == c->rasGen && z.y0 == a.y0 && z.y1 == a.y1;
+    if (bandSlots) refCap = (size_t)T * (size_t)nTiles;             // worst case: every triangle in every tile
+    else refCap = sized ? z.totalRefs : (size_t)T + (size_t)T / 2;  // known, or a guess corrected below
+    size_t jobCap = (size_t)nTiles + refCap / kSlice + 1;
+    if ((e = c->rasJobs.reserve(sizeof(uint2) * jobCap)) != cudaSuccess) return e;
+    jobCap = c->rasJobs.cap / sizeof(uint2);
+
+    ras_setup_kernel<<<(T + 255) / 256 + (T == 0), 256, 0, s>>>(a, tilesX, nTiles, triWord, ts, counts, tileCount, tileOffset,
+                                                               tileMslot, c->rasJobs.as<uint2>(), (unsigned)jobCap, ctr);
+    c->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+    if (bandSlots) {
+        sampleCap = (size_t)T * 3 * (size_t)bandH;
+        c->rasErrPending = true;  // capacity flag: checked by the caller's next synchronising call (ras_take_error)
+    } else {
+        if (!sized) {
+            // how many large triangles / edge samples / tile-list entries / jobs: 32 bytes back to size the buffers
+            if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+            const RasCounters host = *reinterpret_cast<RasCounters*>(c->pinned);
+            if (host.err) {
+                cudaMemsetAsync(&ctr->sticky, 0, sizeof(unsigned), s);  // reported right here
+                return cudaErrorInvalidValue;
+            }
+            z.valid = true;
+            z.gen = c->rasGen;
+            z.y0 = a.y0;
+            z.y1 = a.y1;
+            z.nBig = host.nBig;
+            z.bigSamples = host.bigSamples;
+            z.totalRefs = host.totalRefs;
+            if (host.totalJobs > jobCap) {  // the guess was short: size the table and rebuild it from the offsets
+                jobCap = (size_t)host.totalJobs;
+                if ((e = c->rasJobs.reserve(sizeof(uint2) * jobCap)) != cudaSuccess) return e;
+                ras_jobs_kernel<<<1, 256, 0, s>>>(tileOffset, tileMslot, c->rasJobs.as<uint2>(), (unsigned)jobCap, nTiles);
+                c->launches++;
+            }
+        } else {
+            c->rasErrPending = true;  // cannot be set for a state that drew cleanly before; kept for symmetry
+        }
+        nBig = z.nBig;
+        nSamples = z.bigSamples;
+        refCap = z.totalRefs;
+        sampleCap = nSamples;
+    }
+    const size_t nJobsMax = std::min(jobCap, (size_t)nTiles + refCap / kSlice + 1);  // grid of ras_tile (surplus CTAs exit)
+    if ((e = c->rasRefs.reserve(sizeof(unsigned) * refCap + 256)) != cudaSuccess) return e;
+    if ((e = c->rasRows.reserve(sizeof(EdgeSample) * sampleCap + 256)) != cudaSuccess) return e;
+    if ((e = c->rasPartials.reserve(sizeof(uint4) * kTilePix * (2 * (refCap / kSlice) + 2))) != cudaSuccess) return e;
+    unsigned* refs = c->rasRefs.as<unsigned>();
+    EdgeSample* samples = c->rasRows.as<EdgeSample>();
+
     if (T > 0) {
-        const size_t smem = sizeof(int) * 8 * kWindowRows * kSmallThreads;
-        static bool attrSet = false;
-        if (!attrSet) {
-            if ((e = cudaFuncSetAttribute(ras_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-            attrSet = true;
-        }
-        if (bandSlots) {  // worst case: every triangle is large
-            const size_t nSlots = (size_t)T * (size_t)bandH;
-            if ((e = c->rasRows.reserve(sizeof(RowRec) * nSlots + sizeof(EdgeSample) * 3 * nSlots + 1024)) != cudaSuccess) return e;
-        }
-        ras_small_kernel<<<(T + kSmallThreads - 1) / kSmallThreads, kSmallThreads, smem, s>>>(a, keys, ts, counts, triInfo, rowRec, ctr);
+        ras_bin_kernel<<<(T + 255) / 256, 256, 0, s>>>(triWord, T, tilesX, ts, tileCount, tileOffset, refs);
         c->launches++;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     if (bandSlots) {
-        const size_t nSlots = (size_t)T * (size_t)bandH;
-        unsigned char* rb = c->rasRows.as<unsigned char>();
-        RowRec* rows = reinterpret_cast<RowRec*>(rb);
-        EdgeSample* samples = reinterpret_cast<EdgeSample*>(rb + align_up(sizeof(RowRec) * nSlots, 256));
-        rowsPtr = rows;
-        ras_edges_kernel<true><<<(15 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, nullptr, a.y0, a.y1);
-        ras_rows_kernel<true><<<(unsigned)((nSlots + 255) / 256), 256, 0, s>>>(ts, ctr, samples, nullptr, 0u, rows, keys, a.W, a.y0,
-                                                                              a.y1, a.stats);
-        c->launches += 2;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        c->rasErrPending = true;  // checked by the caller's next synchronising call (ras_take_error)
-    } else if (T > 0) {
-        // how many large triangles / rows / edge samples: 16 bytes back to size the big path
-        if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-        host = *reinterpret_cast<RasCounters*>(c->pinned);
-        if (host.err) {
-            cudaMemsetAsync(&ctr->sticky, 0, sizeof(unsigned), s);  // reported right here
-            return cudaErrorInvalidValue;
+        if (T > 0) {
+            ras_edges_kernel<true><<<(12 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, a.y0, a.y1);
+            c->launches++;
         }
-    }
-    if (host.nBig > 0) {
-        const int nBig = (int)host.nBig;
-        const unsigned nRows = host.bigRows, nSamples = host.bigSamples;
-        const int nb = (nBig + kScanBlock - 1) / kScanBlock;
-        if ((e = c->rasRows.reserve(sizeof(RowRec) * (size_t)nRows + sizeof(unsigned) * (size_t)nRows +
-                                    sizeof(EdgeSample) * (size_t)nSamples + 1024)) != cudaSuccess)
-            return e;
-        unsigned char* rb = c->rasRows.as<unsigned char>();
-        RowRec* rows = reinterpret_cast<RowRec*>(rb);
-        unsigned* owner = reinterpret_cast<unsigned*>(rb + align_up(sizeof(RowRec) * (size_t)nRows, 256));
-        EdgeSample* samples = reinterpret_cast<EdgeSample*>(reinterpret_cast<unsigned char*>(owner) +
-                                                            align_up(sizeof(unsigned) * (size_t)nRows, 256));
-        rowsPtr = rows;
-        scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, nBig);
+    } else if (nBig > 0) {
+        const int nb = ((int)nBig + kScanBlock - 1) / kScanBlock;
+        scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, (int)nBig);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
-        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
-        ras_edges_kernel<false><<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, ctr, samples, owner, a.y0, a.y1);
-        ras_rows_kernel<false><<<(nRows + 255) / 256, 256, 0, s>>>(ts, ctr, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
-        c->launches += 5;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, (int)nBig);
+        ras_edges_kernel<false><<<(12 * (int)nBig + 127) / 128, 128, 0, s>>>(ts, (int)nBig, ctr, samples, a.y0, a.y1);
+        c->launches += 4;
     }
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
     {
-        dim3 grid((a.W + 256 * kShadePixels - 1) / (256 * kShadePixels), bandH);
-        ras_shade_kernel<<<grid, 256, 0, s>>>(a, ts, triInfo, rowRec, rowsPtr, keys, ctr);
+        TileArgs g;
+        g.tileOffset = tileOffset;
+        g.refs = refs;
+        g.tileCount = tileCount;
+        g.bigTs = ts;
+        g.samples = samples;
+        g.ctr = ctr;
+        g.tileMslot = tileMslot;
+        g.jobTile = c->rasJobs.as<uint2>();
+        g.tileDone = tileDone;
+        g.partials = c->rasPartials.as<uint4>();
+        g.tilesX = tilesX;
+        g.nTiles = nTiles;
+        g.nEpochs = (int)(((long long)T + (1ll << kTriBits) - 1) >> kTriBits);
+        ras_tile_kernel<<<(unsigned)nJobsMax, kTileThreads, 0, s>>>(a, g);
         c->launches++;
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) {
         c->rasCtrDirty = false;
-        c->rasKeysClean = keyBytes;
-        c->rasKeysCleanPtr = keys;
+        c->rasTilesClean = (size_t)nTiles;
     }
     return e;
 }

@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, f
 
 cudaError_t run_fp32_peak(Ctx* c, double* tflops, double* seconds) {
     cudaError_t e;
-    if ((e = c->rasScratch.reserve(1 << 20)) != cudaSuccess) return e;
+    if ((e = c->subScratch.reserve(1 << 20)) != cudaSuccess) return e;
     const int blocks = c->smCount * 8, threads = 256, iters = 4096;
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0);
@@ -225,7 +225,7 @@ cudaError_t run_fp32_peak(Ctx* c, double* tflops, double* seconds) {
     double best = 0.0, bestSec = 0.0;
     for (int rep = 0; rep < 5; ++rep) {
         cudaEventRecord(ev0, c->stream);
-        fp32_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->rasScratch.as<float>(), iters, 0.999f, 0.001f);
+        fp32_peak_kernel<<<blocks, threads, 0, c->stream>>>(c->subScratch.as<float>(), iters, 0.999f, 0.001f);
         cudaEventRecord(ev1, c->stream);
         if ((e = cudaEventSynchronize(ev1)) != cudaSuccess) break;
         float ms = 0.f;

@@ -249,6 +249,52 @@ RasFrame ras_frame_of(const Ctx* c) {
 }
 }  // namespace
 
+
+// ---- self-test of the shared-reciprocal division (exact.cuh: Recip / xdiv_by) -------------------------
+// Compares xdiv_by(a, recip_make(b)) with div.rn.f32 bit for bit on pseudo-random operand pairs: uniformly random bit
+// patterns (every exponent, zeros, denormals, infinities, NaNs), pairs confined to and straddling the [2^-60, 2^60)
+// guard, small integers over small integers (the edge and span steps), values near 1 (pos3d / zinv).
+__device__ __forceinline__ unsigned mix32(unsigned long long z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (unsigned)((z ^ (z >> 31)) >> 16);
+}
+__device__ __forceinline__ float pattern_operand(unsigned r, unsigned mode) {
+    switch (mode) {
+        case 0: return __uint_as_float(r);                                                   // anything
+        case 1: return __uint_as_float((r & 0x807FFFFFu) | ((67u + (r >> 23) % 120u) << 23));  // inside the guard
+        case 2: return __uint_as_float((r & 0x807FFFFFu) | ((60u + (r >> 23) % 16u) << 23));   // around 2^-60
+        case 3: return __uint_as_float((r & 0x807FFFFFu) | ((180u + (r >> 23) % 16u) << 23));  // around 2^60
+        case 4: return (float)((int)(r % 8193u) - 4096);                                     // small integers
+        case 5: return (float)(1 + r % 4096u);                                               // row / step counts
+        default: return __uint_as_float((r & 0x007FFFFFu) | 0x3F000000u | (r & 0x80000000u));  // [0.5, 1)
+    }
+}
+__global__ void division_selftest_kernel(unsigned long long n, unsigned seed, unsigned long long* __restrict__ bad,
+                                         float* __restrict__ firstBad) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long mism = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned r0 = mix32(i * 3 + seed), r1 = mix32(i * 3 + 1 + seed), r2 = mix32(i * 3 + 2 + seed);
+        const unsigned ma = r2 % 7u, mb = (r2 >> 8) % 7u;
+        const float a = pattern_operand(r0, ma), b = pattern_operand(r1, mb);
+        const float want = __fdiv_rn(a, b);
+        const float got = xdiv_by(a, recip_make(b));
+        const bool same = __float_as_uint(want) == __float_as_uint(got) || (want != want && got != got);
+        if (!same) {
+            if (atomicAdd(bad, 1ull) == 0ull) {
+                firstBad[0] = a;
+                firstBad[1] = b;
+                firstBad[2] = want;
+                firstBad[3] = got;
+            }
+            ++mism;
+        }
+    }
+    (void)mism;
+}
+
 extern "C" {
 
 int b2r_rt_closest_intersection_batch(b2r_ctx* ctx, int n, const float* starts, const float* dirs, const int32_t* isLight,
@@ -397,6 +443,27 @@ int b2r_ras_pixel_shader_batch(b2r_ctx* ctx, int n, const void* pixels24, const 
     SCU(cudaMemcpyAsync(outColours3, d + oO, 12 * (size_t)n, cudaMemcpyDeviceToHost, s), "D2H");
     SCU(cudaMemcpyAsync(outFocal, d + oF, 4 * (size_t)n, cudaMemcpyDeviceToHost, s), "D2H");
     SCU(cudaStreamSynchronize(s), "pixel_shader_batch");
+    return B2R_OK;
+}
+
+int b2r_selftest_division(b2r_ctx* ctx, unsigned long long n, unsigned seed, unsigned long long* mismatches, float* firstBad4) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !mismatches) return B2R_E_INVALID;
+    SCU(cudaSetDevice(c->device), "cudaSetDevice");
+    SCU(c->subScratch.reserve(256), "scratch alloc");
+    char* d = c->subScratch.as<char>();
+    cudaStream_t s = c->stream;
+    SCU(cudaMemsetAsync(d, 0, 64, s), "clear");
+    division_selftest_kernel<<<c->smCount * 8, 256, 0, s>>>(n, seed, (unsigned long long*)d, (float*)(d + 16));
+    c->launches++;
+    SCU(cudaGetLastError(), "division_selftest_kernel");
+    unsigned long long hostBad = 0;
+    float fb[4] = {0, 0, 0, 0};
+    SCU(cudaMemcpyAsync(&hostBad, d, 8, cudaMemcpyDeviceToHost, s), "D2H");
+    SCU(cudaMemcpyAsync(fb, d + 16, 16, cudaMemcpyDeviceToHost, s), "D2H");
+    SCU(cudaStreamSynchronize(s), "division selftest");
+    *mismatches = hostBad;
+    if (firstBad4) memcpy(firstBad4, fb, sizeof fb);
     return B2R_OK;
 }
 

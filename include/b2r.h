@@ -217,6 +217,12 @@ enum {
 int b2r_set_option(b2r_ctx* ctx, int option, int value);
 /* Device FP32 FFMA throughput microbenchmark (TFLOP/s), the raytracer's roofline denominator. */
 int b2r_measure_fp32_peak(b2r_ctx* ctx, double* tflops, double* seconds);
+/* Self-test of the rasteriser's shared-reciprocal IEEE division (several a/b with one b, used for pos/pos.z of
+ * VertexShader rasteriser.cpp:538-541, the step divisions of Interpolate :622-624 and Bresenham :648-649, and
+ * pos3d/zinv of PixelShader :557): n pseudo-random operand pairs (all exponents, zeros, denormals, infinities, NaN,
+ * small integers) against div.rn.f32, bit for bit.  *mismatches must come back 0; firstBad4 (optional) receives
+ * a, b, expected, got of the first mismatch. */
+int b2r_selftest_division(b2r_ctx* ctx, unsigned long long n, unsigned seed, unsigned long long* mismatches, float* firstBad4);
 
 /* ---- single-frame split across GPUs: resolve fused with the band exchange ---- */
 /* One process per GPU.  Each rank renders its row band (y0,y1 of the draw calls) and resolves it
