@@ -168,7 +168,7 @@ int b2r_destroy(b2r_ctx* ctx) {
     cudaSetDevice(c->device);
     if (c->ownStream) cudaStreamSynchronize(c->ownStream);
     DevBuf* bufs[] = {&c->raw, &c->culled, &c->geom, &c->frame, &c->colours, &c->closest, &c->focal, &c->depth,
-                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasRefs, &c->rasScratch, &c->rasJobs, &c->rasPartials, &c->raw64, &c->rtX, &c->rtF, &c->rtSched, &c->subScratch, &c->stats};
+                      &c->winner, &c->surface, &c->bgr, &c->rasTri, &c->rasRows, &c->rasRefs, &c->rasScratch, &c->rasJobs, &c->rasPartials, &c->raw64, &c->rasSLScratch, &c->rasKeys, &c->rasSmall, &c->rtX, &c->rtF, &c->rtSched, &c->subScratch, &c->stats};
     for (DevBuf* b : bufs) b->release();
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->pinnedFrame) cudaFreeHost(c->pinnedFrame);

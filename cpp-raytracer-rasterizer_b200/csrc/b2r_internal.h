@@ -187,7 +187,8 @@ struct Ctx {
     // outputs kept on the device between draw and resolve / host copies
     DevBuf colours, closest, focal, depth, winner, surface, bgr;
     // rasteriser intermediates
-    DevBuf rasTri, rasRows, rasRefs, rasScratch, rasJobs, rasPartials;  // triangle words + large-triangle records, edge samples, tile lists, counters
+    DevBuf rasTri, rasRows, rasRefs, rasScratch, rasJobs, rasPartials;
+    DevBuf rasSLScratch, rasKeys, rasSmall;  // sort-last pipeline: counters + scan scratch, key buffer, small-triangle row records  // triangle words + large-triangle records, edge samples, tile lists, counters
     DevBuf subScratch;  // staging of the sub-stage entry points
     struct KernelInfo {
         const void* fn;
@@ -199,6 +200,12 @@ struct Ctx {
     void* waitValue32 = nullptr;  // cuStreamWaitValue32 when the driver offers stream memory operations
     bool memOpsProbed = false;
     DevBuf rtX, rtF;  // raytracer, scenes too large for shared memory: per-frame (origin,triangle) constants
+    size_t rasKeysClean = 0;          // bytes of rasKeys known to be zero (left so by the last shade pass)
+    void* rasKeysCleanPtr = nullptr;
+    bool rasSmallAttr = false;        // ras_small's shared-memory opt-in has been set on this context's device
+    bool rasSLCtrDirty = true;        // the sort-last pipeline's per-frame counters need a clear before the next draw
+    void* rasErrCtr = nullptr;        // counters (RasCounters) of the pipeline whose capacity flag is pending
+    bool rasTileAttr = false;         // ras_tile's shared-memory opt-in has been set on this context's device
     size_t rasTilesClean = 0;         // tile counts known to be zero for a grid of this many tiles (left so by ras_tile)
     // Buffer sizes of the rasteriser's large-scene path, read back once per (scene, culling flags, frame params, band):
     // rasGen counts the changes of the first three.

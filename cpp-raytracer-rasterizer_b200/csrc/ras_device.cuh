@@ -32,6 +32,18 @@ __device__ __forceinline__ float xdiv_step_by(float a, const Recip& d) {
     return xdiv_by(a, d);
 }
 
+// Branch-free form for a group of step divisions by one small positive integer b (edge steps :622-624, span steps
+// :648-649): the fast sequence is evaluated unconditionally -- it is exact for b == 1 (r == 1) -- a zero numerator gets
+// its signed zero, and `ok` collects whether every non-zero numerator was inside the fast path's range; the caller
+// redoes the group with xdiv_step() when it was not (practically never).
+__device__ __forceinline__ float xdiv_step_fast(float a, const Recip& d, bool& ok) {
+    const float q0 = __fmul_rn(a, d.r);
+    const float q = __fmaf_rn(d.r, __fmaf_rn(-d.b, q0, a), q0);
+    const bool zero = a == 0.0f;
+    ok = ok && (zero || div_safe(a));
+    return zero ? __int_as_float((__float_as_int(a) ^ __float_as_int(d.b)) & 0x80000000) : q;
+}
+
 struct RPixel {  // == struct Pixel (rasteriser TestModel.h:34-53)
     int x, y;
     float zinv;

@@ -1,4 +1,5 @@
-// ras_pipeline.cu -- the rasteriser hot path on sm_100a.
+// ras_tiles.cu -- the rasteriser hot path on sm_100a, screen-tile form (B2R_OPT_RAS_VARIANT = 2), plus what both
+// pipelines share on the host side (culling, the 64-byte scene copy, the deferred error flag, the dispatcher).
 //
 // Replaces Draw() -> DrawPolygon() -> VertexShader / ComputePolygonRows /
 // Interpolate / DrawRows / DrawLineSDL / Bresenham / PixelShader of
@@ -46,6 +47,7 @@
 #include "b2r_internal.h"
 #include "exact.cuh"
 #include "pixel_pack.cuh"
+#include "ras_common.cuh"
 #include "ras_device.cuh"
 
 namespace b2r {
@@ -82,11 +84,6 @@ struct EdgeSample {  // one Interpolate() result entry (:628-631) without y (imp
     float zinv, px, py;
 };
 
-struct RasCounters {
-    unsigned nBig, bigRows, bigSamples, err, totalRefs, blocksDone, totalJobs, pad0;  // per frame, re-armed by ras_tile
-    unsigned sticky;  // like err, but only cleared by the host after it has been reported (asynchronous draws)
-    unsigned pad1[7];
-};
 
 // How far int(current.x) of an edge walk can lie outside the vertices' x range: the chain a.x + step + step + ...
 // drifts from the exact line by at most one ulp of the largest magnitude per step (half from the addition, half
@@ -120,59 +117,74 @@ __device__ __forceinline__ void count_tile(unsigned* __restrict__ tileCount, int
 template <bool FROM_OFFSETS>
 __device__ void tile_scan_block(unsigned* __restrict__ tileCount, unsigned* __restrict__ tileOffset, unsigned* __restrict__ tileMslot,
                                 uint2* __restrict__ jobTile, unsigned jobCap, int nTiles, RasCounters* __restrict__ ctr) {
+    constexpr int kChunk = 256 * 16;  // tiles staged in shared memory at a time (coalesced loads, all in flight)
+    __shared__ unsigned cnt[kChunk];
     __shared__ unsigned warpSums[3][8];
+    __shared__ unsigned carry[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (nTiles + 255) / 256, t0 = min(tid * per, nTiles), t1 = min(t0 + per, nTiles);
-    unsigned sum[3] = {0u, 0u, 0u};  // entries, jobs, partial slots
-    for (int t = t0; t < t1; ++t) {
-        const unsigned v = FROM_OFFSETS ? __ldcg(&tileOffset[t + 1]) - __ldcg(&tileOffset[t]) : __ldcg(&tileCount[t]);
-        const unsigned k = max(1u, (v + kSlice - 1) / kSlice);
-        sum[0] += v;
-        sum[1] += k;
-        sum[2] += (k > 1u) ? k : 0u;
-    }
-    unsigned run[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        unsigned inc = sum[c];
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned x = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc += x;
+    if (tid < 3) carry[tid] = 0u;
+    for (int c0 = 0; c0 < nTiles; c0 += kChunk) {
+        const int nc = min(kChunk, nTiles - c0);
+        __syncthreads();
+        for (int t = tid; t < nc; t += 256)
+            cnt[t] = FROM_OFFSETS ? __ldcg(&tileOffset[c0 + t + 1]) - __ldcg(&tileOffset[c0 + t]) : __ldcg(&tileCount[c0 + t]);
+        __syncthreads();
+        const int per = (nc + 255) / 256, t0 = min(tid * per, nc), t1 = min(t0 + per, nc);
+        unsigned sum[3] = {0u, 0u, 0u};  // entries, jobs, partial slots
+        for (int t = t0; t < t1; ++t) {
+            const unsigned v = cnt[t], k = max(1u, (v + kSlice - 1) / kSlice);
+            sum[0] += v;
+            sum[1] += k;
+            sum[2] += (k > 1u) ? k : 0u;
         }
-        if (lane == 31) warpSums[c][warp] = inc;
-        run[c] = inc - sum[c];
+        unsigned run[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            unsigned inc = sum[c];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned x = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += x;
+            }
+            if (lane == 31) warpSums[c][warp] = inc;
+            run[c] = inc - sum[c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            run[c] += carry[c];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k < warp) run[c] += warpSums[c][k];
+        }
+        for (int t = t0; t < t1; ++t) {
+            const unsigned v = cnt[t], k = max(1u, (v + kSlice - 1) / kSlice);
+            if (!FROM_OFFSETS) {
+                tileOffset[c0 + t] = run[0];
+                tileCount[c0 + t] = 0u;
+            }
+            tileMslot[c0 + t] = run[2];
+            for (unsigned sl = 0; sl < k; ++sl)
+                if (run[1] + sl < jobCap) jobTile[run[1] + sl] = make_uint2((unsigned)(c0 + t), sl);  // a short table is rebuilt by ras_jobs
+            run[0] += v;
+            run[1] += k;
+            run[2] += (k > 1u) ? k : 0u;
+        }
+        __syncthreads();
+        if (tid == 255) {  // owns the chunk's last tiles: its running sums are the chunk totals
+            carry[0] = run[0];
+            carry[1] = run[1];
+            carry[2] = run[2];
+        }
     }
     __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (k < warp) run[c] += warpSums[c][k];
-    for (int t = t0; t < t1; ++t) {
-        unsigned v;
-        if (FROM_OFFSETS) {
-            v = __ldcg(&tileOffset[t + 1]) - __ldcg(&tileOffset[t]);
-        } else {
-            v = __ldcg(&tileCount[t]);
-            tileOffset[t] = run[0];
-            tileCount[t] = 0u;
-        }
-        const unsigned k = max(1u, (v + kSlice - 1) / kSlice);
-        tileMslot[t] = run[2];
-        for (unsigned sl = 0; sl < k; ++sl)
-            if (run[1] + sl < jobCap) jobTile[run[1] + sl] = make_uint2((unsigned)t, sl);  // a short table is rebuilt by ras_jobs
-        run[0] += v;
-        run[1] += k;
-        run[2] += (k > 1u) ? k : 0u;
-    }
-    if (tid == 255) {
+    if (tid == 0) {
         if (!FROM_OFFSETS) {
-            tileOffset[nTiles] = run[0];
-            ctr->totalRefs = run[0];
-            ctr->totalJobs = run[1];
+            tileOffset[nTiles] = carry[0];
+            ctr->totalRefs = carry[0];
+            ctr->totalJobs = carry[1];
         }
-        tileOffset[nTiles + 1] = run[1];
+        tileOffset[nTiles + 1] = carry[1];
     }
 }
 
@@ -187,10 +199,12 @@ __global__ void __launch_bounds__(256) ras_setup_kernel(RasLaunch a, int tilesX,
                                                         unsigned* __restrict__ tileCount, unsigned* __restrict__ tileOffset,
                                                         unsigned* __restrict__ tileMslot, uint2* __restrict__ jobTile,
                                                         unsigned jobCap, RasCounters* __restrict__ ctr) {
-    const int i = blockIdx.x * 256 + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    unsigned word = kNoRect;
     unsigned long long nRows = 0, nDrawn = 0;
+    // a CTA walks blocks of 256 triangles (grid = a few CTAs per SM): one fence + ticket per CTA at the end
+    for (int blk = blockIdx.x; blk * 256 < a.T; blk += gridDim.x) {
+    const int i = blk * 256 + threadIdx.x;
+    unsigned word = kNoRect;
     int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
     bool big = false;
     float t[12];
@@ -217,8 +231,8 @@ __global__ void __launch_bounds__(256) ras_setup_kernel(RasLaunch a, int tilesX,
             atomicExch(&ctr->err, 1u);  // the reference would try to allocate/walk an absurd row count
             atomicExch(&ctr->sticky, 1u);
         } else {
-            nDrawn = 1;
-            nRows = (unsigned long long)rows;
+            nDrawn += 1;
+            nRows += (unsigned long long)rows;
             // conservative rectangle of the fragments (x = lx+1 .. rx of every row), clipped to the screen and the band
             const int m = coord_margin(rows, max(abs(minX), abs(maxX)));
             const int xa = max(minX - m, 0), xb = min(maxX + m, a.W - 1);
@@ -273,6 +287,7 @@ __global__ void __launch_bounds__(256) ras_setup_kernel(RasLaunch a, int tilesX,
         const int w = bx1 - bx0 + 1, n = w * (by1 - by0 + 1);
         for (int k = lane; k < n; k += 32) atomicAdd(&tileCount[(by0 + k / w) * tilesX + bx0 + k % w], 1u);
     }
+    }
     if (a.stats) {
         for (int off = 16; off > 0; off >>= 1) {
             nRows += __shfl_xor_sync(0xffffffffu, nRows, off);
@@ -285,9 +300,11 @@ __global__ void __launch_bounds__(256) ras_setup_kernel(RasLaunch a, int tilesX,
     }
     // the last CTA to get here turns the tile counts into list offsets (no separate launch)
     __shared__ bool isLast;
-    __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) isLast = atomicAdd(&ctr->blocksDone, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence();  // cumulative: orders this CTA's counts (made visible to this thread by the barrier) before the ticket
+        isLast = atomicAdd(&ctr->blocksDone, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (isLast) {
         __threadfence();
@@ -501,15 +518,15 @@ struct RowRec {  // what PixelShader needs from the winning row: Bresenham's pos
     int lx;
     float lpx, psx, lpy, psy;
     unsigned tri;
-    int pad[2];
 };
 
 constexpr int kPixPerThread = kTilePix / kTileThreads;  // 4: pixel p = tid + 256 i, a warp covers one tile row
+constexpr int kRoundRows = 384;                         // row items per round (up to two per thread in A3)
 
 struct __align__(16) TileShared {
-    float4 samples[3 * kTileThreads];  // W -> A3: (int x, zinv, pos3d.x, pos3d.y) of row item r, edge e at [3r + e]
+    float4 samples[3 * kRoundRows];    // W -> A3: (int x, zinv, pos3d.x, pos3d.y) of row item r, edge e at [3r + e]
     unsigned long long key[kTilePix];  // depth keys, 0 = nothing drawn (depthBuffer = 0, :188)
-    RowRec rec[kTileThreads];          // A3 -> G: the round's row items
+    RowRec rec[kRoundRows];            // A3 -> G: the round's row items
     // the triangles of the current batch, one per thread (VertexShader output)
     int vy[3][kTileThreads], vx[3][kTileThreads];
     float vz[3][kTileThreads], vpx[3][kTileThreads], vpy[3][kTileThreads];
@@ -517,13 +534,15 @@ struct __align__(16) TileShared {
     unsigned sbase[kTileThreads];  // large triangle: where its edge samples start; kSmallTri otherwise
     int yA[kTileThreads];          // first row inside the tile
     unsigned rowBase[kTileThreads + 4];  // exclusive prefix sum of the rows inside the tile
-    unsigned short rowTri[kTileThreads]; // row item of the current round -> triangle slot of the batch
+    unsigned short rowTri[kRoundRows];   // row item of the current round -> triangle slot of the batch
     unsigned warpSums[8];
 };
-static_assert(sizeof(TileShared) <= 48 * 1024, "ras_tile uses static shared memory");
+static_assert(sizeof(TileShared) <= 55 * 1024 + 768, "four CTAs per SM");
+static_assert(kRoundRows <= (1 << kSlotBits), "row item must fit the key's slot field");
 
-__global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, TileArgs g) {
-    __shared__ TileShared S;
+__global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, TileArgs g) {
+    extern __shared__ __align__(16) unsigned char tileSmem[];
+    TileShared& S = *reinterpret_cast<TileShared*>(tileSmem);
     __shared__ bool lastJob;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (blockIdx.x >= g.tileOffset[g.nTiles + 1]) return;  // the grid is sized for the worst case
@@ -620,11 +639,11 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                 if (tid == kTileThreads - 1) S.rowBase[kTileThreads] = wbase + inc;
                 __syncthreads();
             }
-            // ---- rounds of whole triangles with at most 256 row items between them ----
+            // ---- rounds of whole triangles with at most kRoundRows row items between them ----
             int ja = 0;
             while (ja < nb) {
                 const unsigned base = S.rowBase[ja];
-                const bool fits = tid >= ja && tid < nb && S.rowBase[tid + 1] - base <= (unsigned)kTileThreads;
+                const bool fits = tid >= ja && tid < nb && S.rowBase[tid + 1] - base <= (unsigned)kRoundRows;
                 const int nt = __syncthreads_count(fits);  // >= 1: one triangle has at most kTileH rows in the tile
                 const int jb = ja + nt;
                 const int nrows = (int)(S.rowBase[jb] - base);
@@ -664,10 +683,18 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                     const Recip div = recip_make((float)max(n - 1, 1));  // :622
                     const int ax = S.vx[e][j];
                     float cx = (float)ax, cz = S.vz[e][j], cpx = S.vpx[e][j], cpy = S.vpy[e][j];  // fPixel(Pixel&)
-                    const float sx = xdiv_step_by((float)(S.vx[e2][j] - ax), div);  // Pixel operator- / fPixel operator/
-                    const float sz = xdiv_step_by(xsub(S.vz[e2][j], cz), div);
-                    const float spx = xdiv_step_by(xsub(S.vpx[e2][j], cpx), div);
-                    const float spy = xdiv_step_by(xsub(S.vpy[e2][j], cpy), div);
+                    const float dx = (float)(S.vx[e2][j] - ax), dz = xsub(S.vz[e2][j], cz);  // Pixel operator-
+                    const float dpx = xsub(S.vpx[e2][j], cpx), dpy = xsub(S.vpy[e2][j], cpy);
+                    bool ok = div.ok;
+                    float sx = xdiv_step_fast(dx, div, ok), sz = xdiv_step_fast(dz, div, ok);  // fPixel operator/
+                    float spx = xdiv_step_fast(dpx, div, ok), spy = xdiv_step_fast(dpy, div, ok);
+                    if (!ok) {
+                        sx = xdiv_step(dx, div.b);
+                        sz = xdiv_step(dz, div.b);
+                        spx = xdiv_step(dpx, div.b);
+                        spy = xdiv_step(dpy, div.b);
+                    }
+#pragma unroll 1
                     for (int k = 0; k < kLo; ++k) {  // :626-636, serial accumulation
                         cx = xadd(cx, sx);
                         cz = xadd(cz, sz);
@@ -676,6 +703,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                     }
                     int idx = 3 * (rj + (ya + sgn * kLo - yLo)) + e;
                     const int stride = 3 * sgn;
+#pragma unroll 1
                     for (int k = kLo; k <= kHi; ++k, idx += stride) {
                         // int(current.x): the chain stays within coord_margin of the vertex range, which passed the
                         // +-2^24 limit, so the plain truncating conversion equals the x86 one
@@ -688,9 +716,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                 }
                 __syncthreads();
                 // ---- A3: ComputePolygonRows' resolve (:705-733) + DrawRows / DrawLineSDL / Bresenham (dy == 0) ----
-                if (tid < nrows) {
-                    const int j = S.rowTri[tid];
-                    const int y = S.yA[j] + tid - (int)(S.rowBase[j] - base);
+                for (int ri = tid; ri < nrows; ri += kTileThreads) {
+                    const int j = S.rowTri[ri];
+                    const int y = S.yA[j] + ri - (int)(S.rowBase[j] - base);
                     const unsigned sb = S.sbase[j];
                     int lx = INT_MAX, rx = -INT_MAX;  // :696-697
                     float lz = 0.f, rz = 0.f, lpx = 0.f, lpy = 0.f, rpx = 0.f, rpy = 0.f;
@@ -702,7 +730,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                         if (y >= min(ya, yb) && y <= max(ya, yb)) {
                             float4 q;
                             if (sb == kSmallTri) {
-                                q = S.samples[3 * tid + e];
+                                q = S.samples[3 * ri + e];
                             } else {
                                 const unsigned at = a.bandSlots ? sb + (unsigned)(e * bandH + (y - a.y0)) : off + (unsigned)abs(y - ya);
                                 q = *reinterpret_cast<const float4*>(g.samples + at);
@@ -721,17 +749,23 @@ __global__ void __launch_bounds__(kTileThreads, 3) ras_tile_kernel(RasLaunch a, 
                     const int i0 = max(0, X0 - lx - 1), i1 = min(pixels, X1 - lx - 1);  // :663 keeps 0 <= x < W; here: the tile's columns
                     if (i1 > i0) {
                         const Recip fdx = recip_make((float)pixels);
-                        const float zstep = xdiv_step_by(xsub(rz, lz), fdx);  // :648 (constant-depth rows: 0/n)
+                        const float dz = xsub(rz, lz), dpx = xsub(rpx, lpx), dpy = xsub(rpy, lpy);
+                        bool ok = fdx.ok;
+                        float zstep = xdiv_step_fast(dz, fdx, ok);  // :648 (constant-depth rows: 0/n)
                         RowRec r;
                         r.lx = lx;
                         r.lpx = lpx;
                         r.lpy = lpy;
-                        r.psx = xdiv_step_by(xsub(rpx, lpx), fdx);            // :649
-                        r.psy = xdiv_step_by(xsub(rpy, lpy), fdx);
+                        r.psx = xdiv_step_fast(dpx, fdx, ok);       // :649
+                        r.psy = xdiv_step_fast(dpy, fdx, ok);
+                        if (!ok) {
+                            zstep = xdiv_step(dz, fdx.b);
+                            r.psx = xdiv_step(dpx, fdx.b);
+                            r.psy = xdiv_step(dpy, fdx.b);
+                        }
                         r.tri = S.tri[j];
-                        r.pad[0] = r.pad[1] = 0;
-                        S.rec[tid] = r;
-                        const unsigned lo = ((kTriMask - (r.tri & kTriMask)) << kSlotBits) | (unsigned)tid;
+                        S.rec[ri] = r;
+                        const unsigned lo = ((kTriMask - (r.tri & kTriMask)) << kSlotBits) | (unsigned)ri;
                         unsigned long long* krow = S.key + ((y - Y0) * kTileW - X0 + lx + 1);  // pixel of fragment q: krow[q]
                         for (int q = i0; q < i1; ++q) {
                             const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
@@ -941,7 +975,8 @@ constexpr size_t kBandRefLimit = 1u << 20;   // tile-list entries (T * tiles)
 cudaError_t ras_take_error(Ctx* c) {
     if (!c->rasErrPending) return cudaSuccess;
     c->rasErrPending = false;
-    RasCounters* ctr = c->rasScratch.as<RasCounters>();
+    RasCounters* ctr = reinterpret_cast<RasCounters*>(c->rasErrCtr);  // of the pipeline that drew last
+    if (!ctr) return cudaSuccess;
     unsigned* flag = reinterpret_cast<unsigned*>(c->pinned);
     cudaError_t e = cudaMemcpyAsync(flag, &ctr->sticky, sizeof *flag, cudaMemcpyDeviceToHost, c->stream);
     if (e != cudaSuccess) return e;
@@ -951,7 +986,16 @@ cudaError_t ras_take_error(Ctx* c) {
     return e != cudaSuccess ? e : cudaErrorInvalidValue;
 }
 
-cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
+cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s);
+static cudaError_t launch_ras_draw_tiles(Ctx* c, const RasLaunch& a0, cudaStream_t s);
+
+// B2R_OPT_RAS_VARIANT: 0 sort-last pipeline (default), 1 the same without fixed-capacity slots, 2 screen tiles,
+// 3 screen tiles without fixed-capacity slots.  Every variant produces the same bits.
+cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a, cudaStream_t s) {
+    return c->optRasVariant >= 2 ? launch_ras_draw_tiles(c, a, s) : launch_ras_draw_sortlast(c, a, s);
+}
+
+static cudaError_t launch_ras_draw_tiles(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     RasLaunch a = a0;
     const int T = a.T;
     const int bandH = a.y1 - a.y0;
@@ -987,7 +1031,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     TriSetup* ts = reinterpret_cast<TriSetup*>(c->rasTri.as<unsigned char>() + align_up(sizeof(unsigned) * (size_t)(T + 1), 256));
 
     const bool bandSlots = (size_t)T * (size_t)bandH <= kBandSlotLimit && (size_t)T * (size_t)nTiles <= kBandRefLimit &&
-                           c->optRasVariant != 1;
+                           c->optRasVariant != 3;
     a.bandSlots = bandSlots ? 1 : 0;
     // the per-frame counters and the tile counts are left clear by the previous frame's tile kernel; clear them here
     // only after a draw that did not get that far, on a fresh buffer, or when the tile grid changed shape
@@ -1010,7 +1054,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     if ((e = c->rasJobs.reserve(sizeof(uint2) * jobCap)) != cudaSuccess) return e;
     jobCap = c->rasJobs.cap / sizeof(uint2);
 
-    ras_setup_kernel<<<(T + 255) / 256 + (T == 0), 256, 0, s>>>(a, tilesX, nTiles, triWord, ts, counts, tileCount, tileOffset,
+    ras_setup_kernel<<<std::max(1, std::min((T + 255) / 256, c->smCount * 5)), 256, 0, s>>>(a, tilesX, nTiles, triWord, ts, counts, tileCount, tileOffset,
                                                                tileMslot, c->rasJobs.as<uint2>(), (unsigned)jobCap, ctr);
     c->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -1018,6 +1062,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
     if (bandSlots) {
         sampleCap = (size_t)T * 3 * (size_t)bandH;
         c->rasErrPending = true;  // capacity flag: checked by the caller's next synchronising call (ras_take_error)
+        c->rasErrCtr = ctr;
     } else {
         if (!sized) {
             // how many large triangles / edge samples / tile-list entries / jobs: 32 bytes back to size the buffers
@@ -1043,6 +1088,7 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
             }
         } else {
             c->rasErrPending = true;  // cannot be set for a state that drew cleanly before; kept for symmetry
+            c->rasErrCtr = ctr;
         }
         nBig = z.nBig;
         nSamples = z.bigSamples;
@@ -1089,7 +1135,11 @@ cudaError_t launch_ras_draw(Ctx* c, const RasLaunch& a0, cudaStream_t s) {
         g.tilesX = tilesX;
         g.nTiles = nTiles;
         g.nEpochs = (int)(((long long)T + (1ll << kTriBits) - 1) >> kTriBits);
-        ras_tile_kernel<<<(unsigned)nJobsMax, kTileThreads, 0, s>>>(a, g);
+        if (!c->rasTileAttr) {  // opt in to > 48 KB of shared memory, once per context (= per device)
+            if ((e = cudaFuncSetAttribute(ras_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared))) != cudaSuccess) return e;
+            c->rasTileAttr = true;
+        }
+        ras_tile_kernel<<<(unsigned)nJobsMax, kTileThreads, sizeof(TileShared), s>>>(a, g);
         c->launches++;
     }
     e = cudaGetLastError();

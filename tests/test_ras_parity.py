@@ -20,9 +20,10 @@ def check(got, want):
     assert np.array_equal(bits(got["focalDistances"]), bits(want["focalDistances"]))
 
 
-@pytest.fixture(params=[0, 1], ids=["slots", "readback"])
+@pytest.fixture(params=[0, 1, 2, 3], ids=["sortlast-slots", "sortlast-readback", "tiles-slots", "tiles-readback"])
 def ras_variant(request):
-    """Large-triangle path: 0 = fixed-capacity slots without readback (small scenes), 1 = counters read back."""
+    """Pipeline (B2R_OPT_RAS_VARIANT): sort-last (0, 1) or screen tiles (2, 3); large-triangle path with fixed-capacity
+    slots and no readback (0, 2: small scenes) or with counters read back (1, 3)."""
     return request.param
 
 
@@ -88,30 +89,34 @@ def test_random_scenes(pkg, oracle, seed, ras_variant):
         assert (got["winner"] < 30).all()
 
 
-def test_tessellated_cornell(pkg, oracle):
+@pytest.mark.parametrize("variant", [0, 2], ids=["sortlast", "tiles"])
+def test_tessellated_cornell(pkg, oracle, variant):
     """BASELINE config 4 shape at reduced size: k=24 tessellation (17,280 triangles) at 640x360."""
     w, h = 640, 360
     tris = pkg.tessellate(pkg.cornell_box(), 24)
     fp = pkg.default_frame_params(1, w, h)
-    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, variant=variant)
     check(got, want)
 
 
-def test_config4_full_size(pkg, oracle):
+@pytest.mark.parametrize("variant", [0, 2], ids=["sortlast", "tiles"])
+def test_config4_full_size(pkg, oracle, variant):
     """BASELINE config 4 at full size: 183x183 tessellation = 1,004,670 triangles at 3840x2160."""
     w, h = 3840, 2160
     tris = pkg.tessellate(pkg.cornell_box(), 183)
     assert len(tris) == 1004670
     fp = pkg.default_frame_params(1, w, h)
-    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h)
+    got, want, culled = draw_both(pkg, oracle, tris, fp, w, h, variant=variant)
     check(got, want)
 
 
-def test_row_bands_equal_full_frame(pkg, oracle):
+@pytest.mark.parametrize("variant", [0, 2], ids=["sortlast", "tiles"])
+def test_row_bands_equal_full_frame(pkg, oracle, variant):
     w, h = 160, 120
     tris = pkg.tessellate(pkg.cornell_box(), 6)
     fp = pkg.default_frame_params(1, w, h)
     ctx = pkg.Context(w, h)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, variant)
     ctx.set_triangles(tris)
     ctx.set_frame(fp)
     ctx.ras_cull()
@@ -127,9 +132,11 @@ def test_row_bands_equal_full_frame(pkg, oracle):
     ctx.close()
 
 
-def test_empty_and_all_culled(pkg, oracle):
+@pytest.mark.parametrize("variant", [0, 2], ids=["sortlast", "tiles"])
+def test_empty_and_all_culled(pkg, oracle, variant):
     w, h = 64, 48
     ctx = pkg.Context(w, h)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, variant)
     ctx.set_triangles(np.zeros((0, 15), np.float32))
     ctx.set_frame(pkg.default_frame_params(1, w, h))
     got = ctx.ras_draw()

@@ -91,7 +91,7 @@ def test_soak_random_frames(pkg, oracle):
         # ---- rasteriser
         tris, fp, w, h = _random_ras_case(pkg, rng)
         ctx = pkg.Context(w, h)
-        ctx.set_option(pkg.capi.OPT_RAS_VARIANT, int(rng.integers(0, 2)))
+        ctx.set_option(pkg.capi.OPT_RAS_VARIANT, int(rng.integers(0, 4)))  # both pipelines, with and without fixed slots
         ctx.set_triangles(tris)
         ctx.set_frame(fp)
         culled = ctx.ras_cull()
