@@ -7,7 +7,7 @@ directory name is not a Python identifier, so import it through
 `__graft_entry__.load_package()` (module name `cpp_raytracer_rasterizer_b200`).
 """
 from . import capi  # noqa: F401
-from .capi import (B2RError, Context, FrameParams, camera_rot_from_yaw, cornell_box,  # noqa: F401
+from .capi import (B2RError, Context, FrameParams, Group, camera_rot_from_yaw, cornell_box,  # noqa: F401
                    default_frame_params, jitter_table, load_library, load_stl, orbit_camera, tessellate, write_bmp)
 
 

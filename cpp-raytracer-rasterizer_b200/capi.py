@@ -100,6 +100,10 @@ SYMBOLS = [
     "b2r_resolve_surface_multi_device_async", "b2r_copy_device_async", "b2r_scene_load_stl",
     "b2r_rt_closest_intersection_batch", "b2r_rt_direct_light_batch", "b2r_ras_vertex_shader_batch",
     "b2r_ras_interpolate", "b2r_ras_compute_polygon_rows", "b2r_ras_pixel_shader_batch",
+    "b2r_rt_frame_gather_device_async", "b2r_stream_wait_value32", "b2r_rt_frame_part", "b2r_rt_frame_part_async",
+    "b2r_rt_frame_bgr8_async", "b2r_ras_frame_part_async",
+    "b2r_group_create", "b2r_group_destroy", "b2r_group_size", "b2r_group_ctx", "b2r_group_last_error",
+    "b2r_group_set_triangles", "b2r_group_set_frame", "b2r_group_rt_frame", "b2r_group_ras_frame", "b2r_group_rt_frames",
 ]
 
 _lib = None
@@ -173,6 +177,24 @@ def load_library():
     lib.b2r_camera_rot_from_yaw.argtypes = [C.c_float, C.c_float, fp]
     lib.b2r_orbit_camera.argtypes = [i32, i32, C.c_float, fp, fp]
     lib.b2r_jitter_table.argtypes = [C.c_uint, fp, fp]
+    lib.b2r_rt_frame_gather_device_async.argtypes = [vp, i32, i32, vp, vp]
+    lib.b2r_stream_wait_value32.argtypes = [vp, vp, C.c_uint]
+    lib.b2r_rt_frame_part.argtypes = [vp, i32, i32, vp]
+    lib.b2r_rt_frame_part_async.argtypes = [vp, i32, i32, vp]
+    lib.b2r_rt_frame_bgr8_async.argtypes = [vp, vp]
+    lib.b2r_ras_frame_part_async.argtypes = [vp, i32, i32, vp]
+    lib.b2r_group_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32, i32, i32]
+    lib.b2r_group_destroy.argtypes = [vp]
+    lib.b2r_group_size.argtypes = [vp]
+    lib.b2r_group_ctx.argtypes = [vp, i32]
+    lib.b2r_group_ctx.restype = vp
+    lib.b2r_group_last_error.argtypes = [vp]
+    lib.b2r_group_last_error.restype = C.c_char_p
+    lib.b2r_group_set_triangles.argtypes = [vp, vp, i32, i32]
+    lib.b2r_group_set_frame.argtypes = [vp, C.POINTER(FrameParams)]
+    lib.b2r_group_rt_frame.argtypes = [vp, vp]
+    lib.b2r_group_ras_frame.argtypes = [vp, vp]
+    lib.b2r_group_rt_frames.argtypes = [vp, C.POINTER(FrameParams), i32, vp, C.c_char_p]
     assert lib.b2r_abi_version() == 1
     _lib = lib
     return lib
@@ -333,6 +355,28 @@ class Context:
         self._chk(self.lib.b2r_rt_frame_split_device_async(self.handle, part, nparts, arr, len(surfaces),
                                                            C.c_void_p(d_colours), C.c_void_p(d_closest), C.c_void_p(d_focal)))
 
+    def rt_frame_gather_device_async(self, part, nparts, d_root_surface, d_arrive=0):
+        """Tile rows part, part+nparts, ... of the frame into ONE surface (the root's); the launch's last thread block
+        adds 1 to *d_arrive when every pixel has landed."""
+        self._chk(self.lib.b2r_rt_frame_gather_device_async(self.handle, part, nparts, C.c_void_p(d_root_surface),
+                                                            C.c_void_p(d_arrive)))
+
+    def stream_wait_value32(self, d_word, value):
+        self._chk(self.lib.b2r_stream_wait_value32(self.handle, C.c_void_p(d_word), value))
+
+    def rt_frame_part(self, part, nparts, surface):
+        """Host side of a split frame: this GPU's tile rows into the caller's full-frame host surface (synchronous)."""
+        self._chk(self.lib.b2r_rt_frame_part(self.handle, part, nparts, _ptr(surface)))
+
+    def rt_frame_part_async(self, part, nparts, surface):
+        self._chk(self.lib.b2r_rt_frame_part_async(self.handle, part, nparts, _ptr(surface)))
+
+    def rt_frame_bgr8_async(self, bgr):
+        self._chk(self.lib.b2r_rt_frame_bgr8_async(self.handle, _ptr(bgr)))
+
+    def ras_frame_part_async(self, y0, y1, surface):
+        self._chk(self.lib.b2r_ras_frame_part_async(self.handle, y0, y1, _ptr(surface)))
+
     def ras_frame_device_async(self, y0, y1, d_surface, d_depth=0, d_colours=0, d_focal=0, d_winner=0):
         self._chk(self.lib.b2r_ras_frame_device_async(self.handle, y0, y1, C.c_void_p(d_surface), C.c_void_p(d_depth),
                                                       C.c_void_p(d_colours), C.c_void_p(d_focal), C.c_void_p(d_winner)))
@@ -435,6 +479,72 @@ class Context:
         t, s = C.c_double(), C.c_double()
         self._chk(self.lib.b2r_measure_fp32_peak(self.handle, C.byref(t), C.byref(s)))
         return t.value, s.value
+
+
+class Group:
+    """b2r_group: several GPUs of one box behind one Draw(), in one process."""
+
+    def __init__(self, width, height, devices):
+        self.lib = load_library()
+        self.w, self.h = int(width), int(height)
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.b2r_group_create(C.byref(h), devs, len(devices), self.w, self.h)
+        if rc != 0:
+            raise B2RError(f"b2r_group_create -> {rc}: {self.lib.b2r_group_last_error(None).decode()}")
+        self.handle = h
+        self.n = len(devices)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.b2r_group_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise B2RError(f"b2r group error {rc}: {self.lib.b2r_group_last_error(self.handle).decode()}")
+
+    def set_triangles(self, tris):
+        tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 15)
+        self._chk(self.lib.b2r_group_set_triangles(self.handle, _ptr(tris), len(tris), 60))
+        self.ntris = len(tris)
+
+    def set_frame(self, fp):
+        self._chk(self.lib.b2r_group_set_frame(self.handle, C.byref(fp)))
+
+    def member_set_option(self, i, opt, value):
+        rc = self.lib.b2r_set_option(self.lib.b2r_group_ctx(self.handle, i), opt, value)
+        if rc != 0:
+            raise B2RError(f"b2r_set_option -> {rc}")
+
+    def member_ras_cull(self, i):
+        rc = self.lib.b2r_ras_cull(self.lib.b2r_group_ctx(self.handle, i), None)
+        if rc != 0:
+            raise B2RError(f"b2r_ras_cull -> {rc}")
+
+    def launch_count(self):
+        return sum(int(self.lib.b2r_launch_count(self.lib.b2r_group_ctx(self.handle, i))) for i in range(self.n))
+
+    def rt_frame(self, surface=None):
+        if surface is None:
+            surface = np.zeros((self.h, self.w), np.uint32)
+        self._chk(self.lib.b2r_group_rt_frame(self.handle, _ptr(surface)))
+        return surface
+
+    def ras_frame(self, surface=None):
+        if surface is None:
+            surface = np.zeros((self.h, self.w), np.uint32)
+        self._chk(self.lib.b2r_group_ras_frame(self.handle, _ptr(surface)))
+        return surface
+
+    def rt_frames(self, frames, surfaces=None, bmp_pattern=None):
+        """frames: list of FrameParams; surfaces: (n, h, w) uint32 array or None; bmp_pattern: e.g. '/tmp/f_%04d.bmp'."""
+        arr = (FrameParams * len(frames))(*frames)
+        self._chk(self.lib.b2r_group_rt_frames(self.handle, arr, len(frames), _ptr(surfaces),
+                                               bmp_pattern.encode() if bmp_pattern else None))
+        return surfaces
 
 
 def write_bmp(path, bgr_payload, w, h):

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <new>
 
 #include "b2r_internal.h"
@@ -374,6 +375,7 @@ struct RtSplit {
     uint32_t* const* peers = nullptr;
     int nPeers = 0;
     int stride = 1, offset = 0;
+    unsigned* arrive = nullptr;  // incremented once when the launch's pixels have landed (gather to a root)
 };
 
 static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
@@ -414,7 +416,7 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
         const int tileRows = (y1 - y0 + 7) / 8;  // of the band; this launch takes every stride-th one
         const int mine = tileRows > a.tileRowOffset ? (tileRows - a.tileRowOffset + a.tileRowStride - 1) / a.tileRowStride : 0;
         a.numTiles = a.tilesX * mine;
-        if (mine == 0) return B2R_OK;
+        if (mine == 0 && !(split && split->arrive)) return B2R_OK;
     }
     a.colours = d_col;
     a.closest = d_clo;
@@ -426,6 +428,8 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
         CU(cudaMemsetAsync(c->rtSched.p, 0, 64 + 4 * kMaxCopyBands, c->stream), "scheduler clear");
     }
     a.sched = c->rtSched.as<unsigned>();
+    a.arrive = split ? split->arrive : nullptr;
+    a.arriveCtr = c->rtSched.as<unsigned>() + 2;
     a.bandDone = bandTileRows > 0 ? c->rtSched.as<unsigned>() + 16 : nullptr;
     a.bandTileRows = bandTileRows > 0 ? bandTileRows : 1;
     a.useFilter = c->optRtFilter;
@@ -588,6 +592,7 @@ int b2r_rt_frame_split_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t
         if (!d_surfaces[i]) return fail(c, B2R_E_INVALID, "rt_frame_split: null destination");
     if (c->params.dofEnabled)
         return fail(c, B2R_E_UNSUPPORTED, "rt_frame_split: depth of field needs the neighbouring rows; draw, exchange pixelColours, then resolve");
+    if (int rc = check_band(c, 0, c->H)) return rc;
     if (int rc = reset_stats(c)) return rc;
     RtSplit sp;
     sp.peers = d_surfaces + 1;
@@ -595,6 +600,86 @@ int b2r_rt_frame_split_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t
     sp.stride = nparts;
     sp.offset = part;
     return rt_launch_band(c, 0, c->H, d_col, d_clo, d_foc, d_surfaces[0], 0, &sp);
+}
+
+int b2r_rt_frame_gather_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t* d_root_surface, uint32_t* d_arrive) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (nparts < 1 || part < 0 || part >= nparts || !d_root_surface)
+        return fail(c, B2R_E_INVALID, "rt_frame_gather: bad arguments (0 <= part < nparts, a destination surface)");
+    if (c->params.dofEnabled)
+        return fail(c, B2R_E_UNSUPPORTED, "rt_frame_gather: depth of field needs the neighbouring rows; draw, exchange pixelColours, then resolve");
+    if (int rc = check_band(c, 0, c->H)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    RtSplit sp;
+    sp.stride = nparts;
+    sp.offset = part;
+    sp.arrive = reinterpret_cast<unsigned*>(d_arrive);
+    return rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, d_root_surface, 0, &sp);
+}
+
+int b2r_stream_wait_value32(b2r_ctx* ctx, const uint32_t* d_word, uint32_t value) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!d_word) return fail(c, B2R_E_INVALID, "stream_wait_value32: null word");
+    if (!c->memOpsProbed) {  // stream memory operations: cuStreamWaitValue32 through the runtime's loader
+        c->memOpsProbed = true;
+        cudaDriverEntryPointQueryResult qr;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && fn)
+            c->waitValue32 = fn;
+        cudaGetLastError();
+    }
+    if (!c->waitValue32) return fail(c, B2R_E_UNSUPPORTED, "stream memory operations (cuStreamWaitValue32) are not available");
+    typedef int (*WaitFn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+    if (reinterpret_cast<WaitFn>(c->waitValue32)(c->stream, (unsigned long long)(uintptr_t)d_word, value, 0u /* GEQ */) != 0)
+        return fail(c, B2R_E_CUDA, "cuStreamWaitValue32 failed");
+    return B2R_OK;
+}
+
+// One part of a frame split over several GPUs, host side: draws tile rows part, part + nparts, ... (8 pixel rows each)
+// and copies exactly those rows into the caller's full-frame host surface -- every GPU over its own PCIe link.
+int b2r_rt_frame_part(b2r_ctx* ctx, int part, int nparts, uint32_t* surface) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (int rc = b2r_rt_frame_part_async(ctx, part, nparts, surface)) return rc;
+    CU(cudaStreamSynchronize(c->stream), "rt_frame_part");
+    return B2R_OK;
+}
+
+int b2r_rt_frame_part_async(b2r_ctx* ctx, int part, int nparts, uint32_t* surface) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (nparts < 1 || part < 0 || part >= nparts || !surface) return fail(c, B2R_E_INVALID, "rt_frame_part: bad arguments");
+    if (c->params.dofEnabled)
+        return fail(c, B2R_E_UNSUPPORTED, "rt_frame_part: depth of field needs the neighbouring rows");
+    if (int rc = check_band(c, 0, c->H)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    const size_t n = (size_t)c->W * c->H;
+    CU(c->surface.reserve(n * 4), "alloc surface");
+    RtSplit sp;
+    sp.stride = nparts;
+    sp.offset = part;
+    if (int rc = rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, c->surface.as<uint32_t>(), 0, &sp)) return rc;
+    // rows of tile row t: [8t, 8t+8); this part owns t = part, part + nparts, ...: a 2-D copy with pitch nparts * 8 rows
+    const int tileRows = (c->H + 7) / 8;
+    const int mine = tileRows > part ? (tileRows - part + nparts - 1) / nparts : 0;
+    if (mine == 0) return B2R_OK;
+    const size_t rowBytes = (size_t)c->W * 4, chunk = 8 * rowBytes, pitch = (size_t)nparts * chunk, first = (size_t)part * chunk;
+    const int lastTile = part + (mine - 1) * nparts;
+    const int lastRows = std::min(8, c->H - lastTile * 8);  // the frame's last tile row may be short
+    const int full = lastRows == 8 ? mine : mine - 1;
+    if (full > 0)
+        CU(cudaMemcpy2DAsync((char*)surface + first, pitch, (const char*)c->surface.p + first, pitch, chunk, (size_t)full,
+                             cudaMemcpyDeviceToHost, c->stream), "D2H copy (tile rows)");
+    if (full < mine) {
+        const size_t off = (size_t)lastTile * chunk;
+        CU(cudaMemcpyAsync((char*)surface + off, (const char*)c->surface.p + off, (size_t)lastRows * rowBytes,
+                           cudaMemcpyDeviceToHost, c->stream), "D2H copy (last tile row)");
+    }
+    c->surfaceValid = false;
+    return B2R_OK;
 }
 
 int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* clo, float* foc) {
@@ -799,7 +884,7 @@ int b2r_pin_host_buffer(b2r_ctx* ctx, void* host, size_t bytes) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
     if (!host || bytes == 0) return fail(c, B2R_E_INVALID, "pin_host_buffer: null buffer");
-    cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterDefault);
+    cudaError_t e = cudaHostRegister(host, bytes, cudaHostRegisterPortable);
     if (e == cudaErrorHostMemoryAlreadyRegistered) {
         cudaGetLastError();
         return B2R_OK;
@@ -875,6 +960,47 @@ int b2r_resolve_bgr8(b2r_ctx* ctx, uint8_t* bgr) {
     CU(cudaMemcpyAsync(bgr, c->bgr.p, payload, cudaMemcpyDeviceToHost, c->stream), "bgr D2H");
     CU(cudaStreamSynchronize(c->stream), "resolve");
     return B2R_OK;
+}
+
+// Draw() of the raytracer for the whole frame straight to the BMP payload: trace (+ resolve), BGR conversion on the
+// device, one D2H copy of 3 bytes per pixel; returns after enqueueing (b2r_synchronize waits).
+int b2r_rt_frame_bgr8_async(b2r_ctx* ctx, uint8_t* bgr) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!bgr) return fail(c, B2R_E_INVALID, "null bgr");
+    if (int rc = check_band(c, 0, c->H)) return rc;
+    if (int rc = reset_stats(c)) return rc;
+    const size_t n = (size_t)c->W * c->H, payload = b2r_bmp_payload_bytes(c->W, c->H);
+    CU(c->surface.reserve(n * 4), "alloc surface");
+    CU(c->bgr.reserve(payload), "alloc bgr");
+    if (!c->params.dofEnabled) {
+        if (int rc = rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, c->surface.as<uint32_t>())) return rc;
+    } else {
+        CU(c->colours.reserve(n * 12), "alloc pixelColours");
+        CU(c->focal.reserve(n * 4), "alloc focalDistances");
+        if (int rc = rt_launch_band(c, 0, c->H, c->colours.as<float>(), nullptr, c->focal.as<float>())) return rc;
+        CU(launch_resolve_surface(c, 0, c->H, c->colours.as<float>(), c->focal.as<float>(), c->surface.as<uint32_t>(), c->stream),
+           "resolve_surface_kernel");
+    }
+    CU(launch_surface_to_bgr8(c, c->surface.as<uint32_t>(), c->bgr.as<uint8_t>(), c->stream), "surface_to_bgr8_kernel");
+    CU(cudaMemcpyAsync(bgr, c->bgr.p, payload, cudaMemcpyDeviceToHost, c->stream), "bgr D2H");
+    c->coloursValid = c->surfaceValid = false;
+    return B2R_OK;
+}
+
+// Rows [y0,y1) of the rasteriser's Draw() into the caller's full-frame host surface; returns after enqueueing.
+int b2r_ras_frame_part_async(b2r_ctx* ctx, int y0, int y1, uint32_t* surface) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (int rc = bind(c)) return rc;
+    if (!surface) return fail(c, B2R_E_INVALID, "null surface");
+    if (int rc = check_band(c, y0, y1)) return rc;
+    if (c->params.dofEnabled)
+        return fail(c, B2R_E_UNSUPPORTED, "ras_frame_part: depth of field needs the neighbouring rows");
+    if (int rc = reset_stats(c)) return rc;
+    CU(c->surface.reserve((size_t)c->W * c->H * 4), "alloc surface");
+    if (int rc = ras_launch_band(c, y0, y1, nullptr, nullptr, nullptr, nullptr, c->surface.as<uint32_t>())) return rc;
+    c->coloursValid = c->surfaceValid = false;
+    return copy_rows_out(c, surface, c->surface.p, y0, y1, 4);
 }
 
 // Headless SDL_SaveBMP: BITMAPFILEHEADER + BITMAPINFOHEADER (54 bytes), 24 bpp, bottom-up.

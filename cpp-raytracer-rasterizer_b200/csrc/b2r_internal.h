@@ -79,6 +79,9 @@ struct RtLaunch {
     unsigned* bandDone;  // may be null: per sub-band, the number of finished warp tiles (host-buffer draw: the copy
                          // stream waits on these words and copies a sub-band out while the kernel is still tracing)
     int bandTileRows;    // tile rows (8 pixel rows each) per sub-band
+    unsigned* arrive;     // may be null: word (usually in another GPU's memory) that the last CTA of this launch increments
+                          // once all of the launch's stores are visible system-wide (single-frame split: gather to a root)
+    unsigned* arriveCtr;  // local word, zero between launches: CTAs that have finished (used with arrive)
     unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
     int batch;         // warp tiles per scheduler fetch (set by the launcher)
     int useFilter;

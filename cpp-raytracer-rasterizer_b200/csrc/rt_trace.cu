@@ -769,6 +769,20 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
         }
     }
 
+    // Gather to a root: the last CTA of this launch tells the root (one increment, over NVLink when the word lives
+    // in a peer's memory) that every pixel of this launch has landed.  Each CTA publishes its own stores first.
+    if (a.arrive) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(a.arriveCtr, 1u) == gridDim.x - 1u) {
+                *a.arriveCtr = 0u;
+                __threadfence_system();
+                atomicAdd_system(a.arrive, 1u);
+            }
+        }
+    }
+
     if constexpr (STATS) {
         unsigned long long v[3] = {cnt.primary, cnt.shadow, cnt.exact};
 #pragma unroll
@@ -797,6 +811,11 @@ static size_t rt_smem_bytes(int T, int nO, int nLights, bool resident, bool cach
 
 constexpr int kMaxDynamicSmem = 200 * 1024;  // launch_rt_trace_shade refuses scenes that need more
 
+__global__ void rt_arrive_kernel(unsigned* arrive) {
+    __threadfence_system();
+    atomicAdd_system(arrive, 1u);
+}
+
 template <bool RESIDENT, bool TILECULL, bool SINGLE = false, bool ONE = false>
 static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaStream_t s) {
     auto kern = a.useFilter ? (a.stats ? rt_trace_shade_kernel<RESIDENT, TILECULL, true, true, SINGLE, ONE>
@@ -819,7 +838,13 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
     }
     int grid = c->smCount * perSM;
     if (grid > a.numTiles) grid = a.numTiles;
-    if (grid < 1) return cudaSuccess;
+    if (grid < 1) {  // nothing to draw: the root still hears from this part
+        if (a.arrive) {
+            rt_arrive_kernel<<<1, 1, 0, s>>>(a.arrive);
+            c->launches++;
+        }
+        return cudaGetLastError();
+    }
     // Warp tiles per scheduler fetch, by the work a tile carries (sub-samples x rays per sub-sample); frames with
     // fewer than 8 tiles per resident warp are strided statically (batch 0).
     RtLaunch b = a;

@@ -1,6 +1,6 @@
 // headless_main.cpp -- the reference's main() loops without SDL: Update(); Draw(); ... SaveBMP.
 //
-//   b2r_headless raytracer  [W H] [--aa N] [--soft] [--dof] [--frames F] [--out prefix]
+//   b2r_headless raytracer  [W H] [--aa N] [--soft] [--dof] [--frames F] [--out prefix] [--gpus N]
 //   b2r_headless rasteriser [W H] [--dof] [--frames F] [--out prefix]
 // With --frames F > 1 the camera orbits the box (yaw = f*2pi/F) and one BMP
 // per frame is written; otherwise a single screenshot like the reference's Esc key (raytracer.cpp:175).
@@ -19,7 +19,7 @@ int main(int argc, char** argv) {
         return 2;
     }
     const bool rt = std::strcmp(argv[1], "raytracer") == 0;
-    int W = 500, H = 500, frames = 1, aa = 0, soft = 0, dof = 0, a = 2;
+    int W = 500, H = 500, frames = 1, aa = 0, soft = 0, dof = 0, a = 2, gpus = 1;
     std::string out = rt ? "raytracer" : "rasteriser";
     if (argc >= 4 && argv[2][0] != '-') {
         W = std::atoi(argv[2]);
@@ -32,8 +32,11 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[a], "--dof")) dof = 1;
         else if (!std::strcmp(argv[a], "--frames") && a + 1 < argc) frames = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--out") && a + 1 < argc) out = argv[++a];
+        else if (!std::strcmp(argv[a], "--gpus") && a + 1 < argc) gpus = std::atoi(argv[++a]);
     }
-    int rc = rt ? rtref::Initialize(W, H, 0) : raref::Initialize(W, H, 0);
+    int devices[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    if (gpus < 1 || gpus > 8) gpus = 1;
+    int rc = rt ? rtref::InitializeDevices(W, H, devices, gpus) : raref::Initialize(W, H, 0);
     if (rc) {
         std::fprintf(stderr, "init failed (%d): %s\n", rc, rt ? rtref::LastError() : raref::LastError());
         return 1;

@@ -33,13 +33,14 @@ std::vector<uint32_t> screenPixels;
 
 namespace {
 b2r_ctx* g_ctx = nullptr;
+b2r_group* g_group = nullptr;  // more than one device: g_ctx is its first member
 const Triangle* g_uploaded = nullptr;
 size_t g_uploadedCount = 0;
 int g_rc = 0;
 float RandomNumber() { return ((double)rand() / (RAND_MAX)) - 0.5f; }  // :260-263
 }  // namespace
 
-const char* LastError() { return b2r_last_error(g_ctx); }
+const char* LastError() { return g_group ? b2r_group_last_error(g_group) : b2r_last_error(g_ctx); }
 
 int Initialize(int width, int height, int device) {
     Shutdown();
@@ -72,7 +73,23 @@ int Initialize(int width, int height, int device) {
     return g_rc;
 }
 
+int InitializeDevices(int width, int height, const int* devices, int n) {
+    if (n <= 1) return Initialize(width, height, n == 1 ? devices[0] : 0);
+    const int rc = Initialize(width, height, devices[0]);  // the globals; its single context is replaced by the group
+    if (rc) return rc;
+    Shutdown();
+    g_rc = b2r_group_create(&g_group, devices, n, width, height);
+    if (g_rc == 0) g_ctx = b2r_group_ctx(g_group, 0);
+    return g_rc;
+}
+
 void Shutdown() {
+    if (g_group) {
+        b2r_group_destroy(g_group);
+        g_group = nullptr;
+        g_ctx = nullptr;
+        return;
+    }
     if (g_ctx) {
         b2r_unpin_host_buffer(g_ctx, screenPixels.data());
         b2r_unpin_host_buffer(g_ctx, pixelColours.data());
@@ -127,7 +144,8 @@ namespace {
 int push_state(const std::vector<Triangle>& tris) {
     if (!g_ctx) return B2R_E_NO_SCENE;
     if (g_uploaded != tris.data() || g_uploadedCount != tris.size()) {
-        int rc = b2r_set_triangles(g_ctx, tris.data(), (int)tris.size(), (int)sizeof(Triangle));
+        int rc = g_group ? b2r_group_set_triangles(g_group, tris.data(), (int)tris.size(), (int)sizeof(Triangle))
+                         : b2r_set_triangles(g_ctx, tris.data(), (int)tris.size(), (int)sizeof(Triangle));
         if (rc) return rc;
         g_uploaded = tris.data();
         g_uploadedCount = tris.size();
@@ -149,12 +167,16 @@ int push_state(const std::vector<Triangle>& tris) {
     p.dofEnabled = DOF_ENABLED;
     p.dofKernelSize = DOF_KERNEL_SIZE;
     p.currentReflectance[0] = p.currentReflectance[1] = p.currentReflectance[2] = 1.0f;
-    return b2r_set_frame(g_ctx, &p);
+    return g_group ? b2r_group_set_frame(g_group, &p) : b2r_set_frame(g_ctx, &p);
 }
 }  // namespace
 
 void Draw() {
     if ((g_rc = push_state(triangles)) != 0) return;
+    if (g_group) {  // rows are the parallel axis (:557-558): here over GPUs
+        g_rc = b2r_group_rt_frame(g_group, screenPixels.data());
+        return;
+    }
     g_rc = b2r_rt_frame(g_ctx, screenPixels.data(), reinterpret_cast<float*>(pixelColours.data()),
                         reinterpret_cast<b2r_intersection*>(closestIntersections.data()), focalDistances.data());
 }
@@ -182,7 +204,21 @@ vec3 DirectLight(const Intersection& i) {
 int SaveBMP(const char* path) {
     if (!g_ctx) return B2R_E_NO_SCENE;
     std::vector<uint8_t> bgr(b2r_bmp_payload_bytes(SCREEN_WIDTH, SCREEN_HEIGHT));
-    int rc = b2r_resolve_bgr8(g_ctx, bgr.data());
+    int rc = 0;
+    if (g_group) {  // the frame is in screenPixels (XRGB): 24-bit bottom-up rows padded to 4 bytes, like SDL_SaveBMP
+        const size_t rowBytes = ((size_t)SCREEN_WIDTH * 3 + 3) & ~(size_t)3;
+        for (int y = 0; y < SCREEN_HEIGHT; ++y) {
+            uint8_t* dst = bgr.data() + (size_t)(SCREEN_HEIGHT - 1 - y) * rowBytes;
+            const uint32_t* src = screenPixels.data() + (size_t)y * SCREEN_WIDTH;
+            for (int x = 0; x < SCREEN_WIDTH; ++x) {
+                dst[3 * x] = (uint8_t)(src[x] & 0xFF);
+                dst[3 * x + 1] = (uint8_t)((src[x] >> 8) & 0xFF);
+                dst[3 * x + 2] = (uint8_t)((src[x] >> 16) & 0xFF);
+            }
+        }
+    } else {
+        rc = b2r_resolve_bgr8(g_ctx, bgr.data());
+    }
     if (rc) return rc;
     return b2r_write_bmp(path, bgr.data(), SCREEN_WIDTH, SCREEN_HEIGHT);
 }

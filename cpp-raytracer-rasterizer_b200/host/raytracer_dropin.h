@@ -41,6 +41,9 @@ extern std::vector<uint32_t> screenPixels;       // screen->pixels of the SDL su
 // Opens the GPU context for a W x H screen and applies the reference's start-up state
 // (main(): :115-116,149-162).  device = CUDA ordinal.  Returns 0 or a B2R_E_* code.
 int Initialize(int width, int height, int device);
+// Several GPUs of one box behind the same Draw(): device i traces tile rows i, i+n, ... of every frame (b2r_group_rt_frame).
+// Draw() then fills screenPixels only -- what the reference shows and saves; the per-pixel arrays stay on the GPUs.
+int InitializeDevices(int width, int height, const int* devices, int n);
 void Shutdown();
 void LoadTestModel(std::vector<Triangle>& out);               // TestModel.h:51-192
 void AddLight(vec3 position, vec3 color, float intensity);    // :180-193 (jitter table from glibc rand())

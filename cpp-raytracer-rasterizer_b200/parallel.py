@@ -6,6 +6,10 @@ are independent.  Two partitionings:
   * row bands: one frame, rank r renders rows [y0,y1) into the full-frame offsets of its buffer, then one
     in-place all-gather assembles the frame on every rank (NCCL over NVLink on GPUs, gloo in the CPU tests).
 """
+import mmap
+import os
+
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -43,3 +47,49 @@ def gather_bands(frame, rank, world, group=None):
             if y1 > y0:
                 dist.broadcast(flat[y0:y1], src=r, group=group)
     return frame
+
+
+class SharedHostFrame:
+    """One full-frame uint32 host surface shared by the ranks of a box (POSIX shared memory under /dev/shm).
+
+    The host side of a single-frame split: every rank page-locks the mapping (Context.pin_host_buffer) and copies only
+    its own tile rows into it (Context.rt_frame_part), each over its own PCIe link.  After the frame array come 64
+    int64 progress words, one per rank, for a host-side "all parts delivered" check without a collective.
+    Rank 0 creates the file; the others open it after a barrier (dist.barrier or any other rendezvous).
+    """
+
+    def __init__(self, width, height, rank, world, tag="0"):
+        self.path = f"/dev/shm/b2r_frame_{tag}_{width}x{height}"
+        self.rank, self.world = rank, world
+        nbytes = width * height * 4 + 64 * 8
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        if world > 1 and dist.is_initialized():
+            dist.barrier()
+        self._f = open(self.path, "r+b")
+        self._mm = mmap.mmap(self._f.fileno(), nbytes)
+        self.frame = np.frombuffer(self._mm, np.uint32, width * height).reshape(height, width)
+        self.progress = np.frombuffer(self._mm, np.int64, 64, offset=width * height * 4)
+
+    def publish(self, step):
+        """This rank's part of frame `step` is in the frame."""
+        self.progress[self.rank] = step
+
+    def wait_all(self, step):
+        """Spin until every rank has published `step` (host memory, no collective)."""
+        while int(self.progress[:self.world].min()) < step:
+            pass
+
+    def close(self):
+        self.frame = self.progress = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass
+        self._f.close()
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

@@ -185,6 +185,25 @@ int b2r_rt_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface,
 int b2r_rt_frame_split_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t* const* d_surfaces, int n,
                                     float* d_pixelColours, b2r_intersection* d_closestIntersections,
                                     float* d_focalDistances);
+/* Gather form of the split: this part's pixels go to ONE surface, normally the root GPU's (local on the root,
+ * peer-mapped elsewhere), so the bytes a part sends fall as 1/nparts.  When d_arrive is not NULL, the last thread
+ * block of the launch adds 1 to that 32-bit word -- usually in the root's memory, over NVLink -- after all of the
+ * launch's stores are visible system-wide; the root orders frames with b2r_stream_wait_value32(word, parts * frames)
+ * on its own stream: no collective and no host round trip. */
+int b2r_rt_frame_gather_device_async(b2r_ctx* ctx, int part, int nparts, uint32_t* d_root_surface, uint32_t* d_arrive);
+/* Makes the context's stream wait (on the GPU front end) until *d_word >= value. */
+int b2r_stream_wait_value32(b2r_ctx* ctx, const uint32_t* d_word, uint32_t value);
+/* Host side of a split frame: draws tile rows part, part + nparts, ... and copies exactly those rows into the
+ * caller's FULL-FRAME host surface (width*height uint32; page-lock it once with b2r_pin_host_buffer).  Each GPU of
+ * a split thus ships height/nparts rows over its own PCIe link.  The _async form returns after enqueueing. */
+int b2r_rt_frame_part(b2r_ctx* ctx, int part, int nparts, uint32_t* surface);
+int b2r_rt_frame_part_async(b2r_ctx* ctx, int part, int nparts, uint32_t* surface);
+/* Whole raytracer frame straight to the 24-bit BMP payload (b2r_bmp_payload_bytes; what SDL_SaveBMP writes,
+ * raytracer.cpp:175): 3 bytes per pixel cross the bus instead of 4.  bgr: host memory.  Returns after enqueueing. */
+int b2r_rt_frame_bgr8_async(b2r_ctx* ctx, uint8_t* bgr);
+/* Rows [y0,y1) of the rasteriser's Draw() into the caller's full-frame host surface.  Returns after enqueueing;
+ * b2r_synchronize also reports B2R_E_CAPACITY. */
+int b2r_ras_frame_part_async(b2r_ctx* ctx, int y0, int y1, uint32_t* surface);
 int b2r_ras_frame_device_async(b2r_ctx* ctx, int y0, int y1, uint32_t* d_surface, float* d_depthBuffer,
                                float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
 /* Resolve rows [y0,y1) of d_pixelColours (+ d_focalDistances when DOF is on) into d_surface. */
@@ -243,6 +262,32 @@ int b2r_shared_close(b2r_ctx* ctx, void* d_ptr);
 int b2r_copy_device_async(b2r_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
 int b2r_resolve_surface_multi_device_async(b2r_ctx* ctx, int y0, int y1, const float* d_pixelColours,
                                            const float* d_focalDistances, uint32_t* const* d_surfaces, int n);
+
+/* ---- several GPUs behind one Draw(): a group of contexts in ONE process ------------------------------ */
+/* The reference's Draw() parallelises image rows with OpenMP (raytracer.cpp:557); a group does the same over GPUs.
+ * b2r_group_create makes one context per listed device (same screen size); scene and frame params are replicated.
+ *   b2r_group_rt_frame    Draw() of the raytracer for one frame: device i traces tile rows i, i+n, ... (interleaved,
+ *                         so every device carries the same mix of rows) and copies its rows into the caller's host
+ *                         surface over its own PCIe link.  No collective: the host surface is the meeting point.
+ *   b2r_group_ras_frame   Draw() of the rasteriser, sort-first: the triangle list is replicated, device i draws the
+ *                         i-th contiguous row band.
+ *   b2r_group_rt_frames   an animation: frame f of `frames` is rendered whole by device f mod n;
+ *                         each finished frame is either copied to surfaces + f*width*height (32-bit XRGB) or, when
+ *                         bmp_pattern is given (a printf pattern with one %d), written as the 24-bit BMP
+ *                         SDL_SaveBMP would write (raytracer.cpp:175) by writer threads while the GPUs go on.
+ * A group is driven by one host thread.  Errors: negative B2R_E_* code, text from b2r_group_last_error. */
+typedef struct b2r_group b2r_group;
+int b2r_group_create(b2r_group** out, const int* devices, int n, int width, int height);
+int b2r_group_destroy(b2r_group* g);
+int b2r_group_size(const b2r_group* g);
+b2r_ctx* b2r_group_ctx(b2r_group* g, int i);  /* member context i (options, statistics); owned by the group */
+const char* b2r_group_last_error(const b2r_group* g);
+int b2r_group_set_triangles(b2r_group* g, const void* triangles, int count, int stride_bytes);
+int b2r_group_set_frame(b2r_group* g, const b2r_frame_params* params);
+int b2r_group_rt_frame(b2r_group* g, uint32_t* surface);
+int b2r_group_ras_frame(b2r_group* g, uint32_t* surface);
+int b2r_group_rt_frames(b2r_group* g, const b2r_frame_params* frames, int nframes, uint32_t* surfaces,
+                        const char* bmp_pattern);
 
 /* ---- sub-stage entry points ------------------------------------------------------------------------- */
 /* The reference's callee functions (raytracer.cpp:105-107, rasteriser.cpp:87-94) on caller-provided inputs:

@@ -69,6 +69,49 @@ def main():
     ctx.synchronize()
     assert torch.equal(tmp, ref_surf), f"rank {rank}: split frame (trace kernel + peer stores) differs from the single-GPU frame"
 
+    # --- gather to the root: every rank stores its tile rows into rank 0's surface only; the last thread block of
+    # each launch bumps an arrival word in rank 0's memory and rank 0's stream waits for it on the GPU (no collective)
+    from oracle import portbind as oracle  # checker only
+    want = oracle.resolve_surface(oracle.rt_draw(pkg.cornell_box(), fp, w, h)["pixelColours"], None)
+    assert np.array_equal(ref_surf.cpu().numpy().view(np.uint32), want), "single-GPU frame differs from the oracle"
+    root_bytes = w * h * 4
+    if rank == 0:
+        gmine, ghandle = ctx.shared_alloc(root_bytes + 256)
+        ctx.copy_device_async(gmine, torch.full((h * w + 64,), -1, dtype=torch.int32, device=dev).data_ptr(), root_bytes + 256)
+        ctx.copy_device_async(gmine + root_bytes, torch.zeros(64, dtype=torch.int32, device=dev).data_ptr(), 256)
+        ctx.synchronize()
+    else:
+        gmine, ghandle = 0, None
+    box = [ghandle]
+    dist.broadcast_object_list(box, src=0)
+    groot = gmine if rank == 0 else ctx.shared_open(box[0])
+    dist.barrier()
+    for frame in range(1, 4):
+        ctx.rt_frame_gather_device_async(rank, world, groot, groot + root_bytes)
+        if rank == 0:
+            ctx.stream_wait_value32(groot + root_bytes, world * frame)
+            ctx.copy_device_async(tmp.data_ptr(), groot, root_bytes)
+            ctx.synchronize()
+            assert np.array_equal(tmp.cpu().numpy().view(np.uint32), want), f"gather to root differs from the oracle (frame {frame})"
+        ctx.synchronize()
+        dist.barrier()
+    if rank != 0:
+        ctx.shared_close(groot)
+    dist.barrier()
+    if rank == 0:
+        ctx.shared_free(gmine)
+
+    # --- host side of the split: every rank copies its own tile rows into ONE page-locked host frame (POSIX shm)
+    shm = par.SharedHostFrame(w, h, rank, world, tag=os.environ.get("MASTER_PORT", "0"))
+    ctx.pin_host_buffer(shm.frame)
+    dist.barrier()
+    ctx.rt_frame_part(rank, world, shm.frame)
+    dist.barrier()
+    assert np.array_equal(shm.frame, want), f"rank {rank}: shared host frame differs from the oracle"
+    dist.barrier()
+    ctx.unpin_host_buffer(shm.frame)
+    shm.close()
+
     # --- NCCL variant (parallel.gather_bands)
     surf = torch.zeros((h, w), dtype=torch.int32, device=dev)
     ctx.resolve_surface_device_async(y0, y1, col.data_ptr(), 0, surf.data_ptr())
