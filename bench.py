@@ -6,23 +6,29 @@
 
 Workload (BASELINE.json config 3, named in config.workload): the Cornell box raytraced at
 3840x2160 with AA 4x4 = 16 sub-samples per pixel and one hard-shadow ray per hit sample.
-A "step" is one Draw() (trace + shade + resolve to the 32-bit surface) of one frame.
+A "step" is one Draw() (trace + shade + resolve to the 32-bit surface) of ONE frame -- at N GPUs the frame is
+split: rank r traces tile rows r, r+N, ... and stores its pixels into the root GPU's surface over NVLink
+(b2r_rt_frame_gather_device_async); the last thread block of every launch bumps an arrival word in the root's
+memory and the root's stream waits for it on the GPU.  No collective, strong scaling.
 metric = Mrays/s, a ray being one ClosestIntersection call (primary + shadow rays actually cast,
 counted by the kernel's own counters in an untimed pass).
 
   value         device-resident: inputs already in HBM, CUDA events around each step on the
                 launching stream, L2 flushed between steps, max over ranks.
-  e2e           the same metric through the host-buffer C ABI call a reference user makes
-                (b2r_set_frame + b2r_rt_frame): frame constants H2D from pinned memory and the
-                32-bit surface D2H to pinned memory inside the timed region.
-  roofline      rt_trace_shade kernel alone: algorithmic flops / mean launch time,
-                against the FP32 FFMA peak measured in this run (MEASURED_PEAKS.json has no FP32 entry).
+  e2e           the same metric through the host-buffer C ABI a reference user calls: b2r_set_frame +
+                b2r_rt_frame (N = 1) / b2r_rt_frame_part (N > 1: every rank copies its own tile rows into ONE
+                page-locked host frame shared by the ranks, each over its own PCIe link); wall clock on rank 0,
+                a step ends when every rank's rows are in the frame.
+  roofline      rt_trace_shade kernel alone: EXECUTED FP32 flops (fadd + fmul + 2 ffma lane-operations per launch,
+                from the tracked ncu capture profiles/r02_rt_trace_exec.json) / the launch time measured here,
+                against the FP32 FFMA peak measured in this run -- a fraction <= 1 by construction.  The
+                brute-force count of SURVEY.md 8d (every ray x every triangle) is kept as
+                algorithmic_speedup_vs_bruteforce: the conservative culling removes 98.5 % of those tests.
+  roofline_rasteriser  BASELINE config 4 (1,004,670 triangles at 4K): algorithmic bytes / frame time against the
+                measured HBM bandwidth, the north star's second roofline.
   cpu_baseline  the reference's own raytracer.cpp (oracle/_ref, compiled from /root/reference)
                 timed on this host's cores on a bounded row sample of the same workload.
-  extra         the other BASELINE configs (rasteriser 500^2 and 4K/1M triangles, raytracer 500^2).
-
-N > 1: one process per GPU, frames partitioned across ranks (no data-path collective, weak
-scaling); extra.band_split reports the single-frame row-band split with an NCCL all-gather.
+  extra         the other BASELINE configs, the weak-scaling (frames per rank) numbers, the other exchange forms.
 """
 import argparse
 import json
@@ -53,15 +59,48 @@ def rt4k_params(pkg):
     return fp
 
 
-# --------------------------------------------------------------------------------------------
-# reference arm / cpu baseline (the only place that may execute oracle/)
-# --------------------------------------------------------------------------------------------
-def cpu_reference_sample(pkg, row_step, steps, warmup):
-    """Times the reference CPU implementation on rows 0, row_step, 2*row_step, ... of the workload."""
+def reference_rt4k_params(pkg):
+    """The same frame params built in Python (raytracer.cpp:33-81,116,162), so that the reference arm never loads
+    libb2r.so: FrameParams is a plain ctypes struct."""
+    fp = pkg.FrameParams()
+    fp.numLights = 1
+    fp.lights[0].position[:] = [0.0, -0.5, -0.7]
+    fp.lights[0].color[:] = [1.0, 1.0, 1.0]
+    fp.lights[0].intensity = 14.0
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    fp.softShadowsSamples = 16
+    fp.dofKernelSize = 8
+    fp.indirectLight[:] = [0.2, 0.2, 0.2]
+    fp.currentReflectance[:] = [1.0, 1.0, 1.0]
+    fp.cameraPos[:] = [0.0, 0.0, -2.0]
+    fp.focalLength = H4K / 2.0
+    fp.cameraRot[:] = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]  # yaw 0: cos 0 = 1, sin 0 = 0, [1][1] = 1
+    fp.dofFocalLength = 1.3
+    return fp
+
+
+def reference_cornell_box():
+    """The 30 triangles of LoadTestModel from the reference itself (oracle/_ref), without libb2r.so."""
+    from oracle import refbind
+    for (w, h) in ((500, 500), (W4K, H4K), (96, 64)):
+        if refbind.available("ras", w, h):
+            ra = refbind.RefRasteriser(w, h)
+            ra.load_test_model()
+            return ra.get_triangles()
+    return None
+
+
+def cpu_reference_sample(pkg, row_step, steps, warmup, standalone=False):
+    """Times the reference CPU implementation on rows 0, row_step, 2*row_step, ... of the workload.
+    standalone: build scene and params without libb2r.so (the reference arm loads only oracle/ objects)."""
     from oracle import refbind, portbind
     cores = os.cpu_count() or 1
-    fp = rt4k_params(pkg)
-    tris = pkg.cornell_box()
+    tris = reference_cornell_box() if standalone else None
+    if tris is None:
+        tris = pkg.cornell_box()
+        fp = rt4k_params(pkg)
+    else:
+        fp = reference_rt4k_params(pkg)
     rows = len(range(0, H4K, row_step))
     # rays of the sample, from the port's counters (identical arithmetic, untimed)
     cnt = portbind.rt_draw(tris, fp, W4K, H4K, 0, H4K, threads=cores, ystep=row_step)
@@ -99,11 +138,11 @@ def run_reference_arm(args, pkg):
     # sample would leave the reference's OpenMP threads unevenly loaded and understate it.
     budget_steps = max(1, args.steps + args.warmup)
     row_step = max(4, -(-4 * budget_steps * 6 // 1200))  # ceil(4 * steps * 0.6 s / 120 s)
-    base = cpu_reference_sample(pkg, row_step=row_step, steps=args.steps, warmup=args.warmup)
+    base = cpu_reference_sample(pkg, row_step=row_step, steps=args.steps, warmup=args.warmup, standalone=True)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": base["value"], "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": base["sample"]},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -162,6 +201,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _load_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
+    except Exception:
+        return None
+
+
 def run_gpu_arm(args, pkg):
     import numpy as np
     import torch
@@ -182,6 +228,7 @@ def run_gpu_arm(args, pkg):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    par = pkg.parallel
 
     stream = torch.cuda.Stream(device=dev)
     tris = pkg.cornell_box()
@@ -195,22 +242,65 @@ def run_gpu_arm(args, pkg):
     d_surf = torch.empty((H4K, W4K), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def frame_device():  # Draw(): trace + shade + PutPixelSDL in one kernel, pixelColours and surface left in HBM
-        ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr(), d_col.data_ptr())
-
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # untimed: ray counts of one frame from the kernel's counters
     ctx.enable_stats(True)
-    frame_device()
+    ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr())
     st = ctx.stats()
     ctx.enable_stats(False)
     rays = st["primary_rays"] + st["shadow_rays"]
     flops = algorithmic_flops(st["primary_rays"], st["shadow_rays"], len(tris), fp.numLights * 1)
+
+    # ---- the step: ONE frame, split over the ranks, gathered on rank 0's GPU -------------------------------------
+    # rank 0 owns the surface and, right behind it, the arrival word; the others map both (CUDA IPC, NVLink)
+    root_bytes = npx * 4
+    if rank == 0:
+        root_mem, handle = ctx.shared_alloc(root_bytes + 256)
+        ctx.copy_device_async(root_mem + root_bytes, torch.zeros(64, dtype=torch.int32, device=dev).data_ptr(), 256)
+        ctx.synchronize()
+    else:
+        root_mem, handle = 0, None
+    if world > 1:
+        box = [handle]
+        dist.broadcast_object_list(box, src=0)
+        root = root_mem if rank == 0 else ctx.shared_open(box[0])
+    else:
+        root = root_mem
+    arrive = root + root_bytes
+    calls = [0]
+
+    def frame_split():
+        # one kernel per rank: traces its interleaved tile rows, stores every pixel into the root's surface; its
+        # last thread block tells the root.  The root's stream then waits (on the GPU) for all N launches.
+        ctx.rt_frame_gather_device_async(rank, world, root, arrive)
+        calls[0] += 1
+        if rank == 0:
+            ctx.stream_wait_value32(arrive, world * calls[0])
+
+    # untimed: the assembled frame must be bit-equal to a frame rank 0 rendered alone
+    barrier()
+    frame_split()
+    barrier()
+    split_verified = None
+    if rank == 0:
+        got = torch.empty((H4K, W4K), dtype=torch.int32, device=dev)
+        ctx.copy_device_async(got.data_ptr(), root, root_bytes)
+        ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr())
+        ctx.synchronize()
+        split_verified = bool(torch.equal(got, d_surf))
+        del got
+    barrier()
 
     def timed_loop(fn, steps, warmup, do_flush=True):
         with torch.cuda.stream(stream):
@@ -234,39 +324,50 @@ def run_gpu_arm(args, pkg):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        t_end = time.perf_counter() + 0.4
-        while time.perf_counter() < t_end:
-            frame_device()
-        torch.cuda.synchronize(dev)
+    nwarm = min(4000, int(400 * world / 1.05))  # ~0.4 s; the same number of calls on every rank (the arrival count must agree)
+    for _ in range(nwarm):
+        frame_split()
+    barrier()
     launches0 = ctx.launch_count()
-    total_ms = timed_loop(frame_device, args.steps, args.warmup)
+    total_ms = allmax(timed_loop(frame_split, args.steps, args.warmup))
     launches = ctx.launch_count() - launches0 - args.warmup
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * rays * args.steps / (total_ms * 1e-3) / 1e6  # whole-job Mrays/s
+    value = rays * args.steps / (total_ms * 1e-3) / 1e6  # Mrays/s of the one frame all ranks work on
 
-    # roofline: the trace kernel alone
-    kern_ms = timed_loop(lambda: ctx.rt_draw_device_async(0, H4K, d_col.data_ptr()), args.steps, 1) / args.steps
+    # roofline: the trace kernel alone (one GPU, whole frame), executed flops from the tracked ncu capture
+    kern_ms = timed_loop(lambda: ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr()), args.steps, 1) / args.steps
     peak_tf, _ = ctx.measure_fp32_peak()
-    achieved_tf = flops / (kern_ms * 1e-3) / 1e12
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "rt_trace_shade_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    execp = _load_json("r02_rt_trace_exec.json") or {}
+    exec_flops = execp.get("executed_fp32_flops_per_launch")
+    exec_tf = exec_flops / (kern_ms * 1e-3) / 1e12 if exec_flops else None
+    algo_tf = flops / (kern_ms * 1e-3) / 1e12
 
-    # e2e: host-buffer C ABI, pinned host memory, H2D of the frame constants + D2H of the surface every step
-    surf_host = torch.empty((H4K, W4K), dtype=torch.int32).pin_memory()
-    surf_np = surf_host.numpy().view(np.uint32)
-    def frame_e2e():
-        ctx.set_frame(fp)
-        ctx.rt_frame(surf_np)
+    # ---- e2e: host-buffer C ABI, every step = frame constants H2D + this rank's rows D2H into the one host frame ----
+    if world > 1:
+        shm = par.SharedHostFrame(W4K, H4K, rank, world, tag=os.environ.get("MASTER_PORT", "0"))
+        ctx.pin_host_buffer(shm.frame)
+        host_frame = shm.frame
+        estep = [0]
+
+        def frame_e2e():
+            ctx.set_frame(fp)
+            ctx.rt_frame_part(rank, world, host_frame)
+            estep[0] += 1
+            shm.publish(estep[0])
+            if rank == 0:
+                shm.wait_all(estep[0])
+        call = "b2r_set_frame + b2r_rt_frame_part (own tile rows into one page-locked host frame shared by the ranks)"
+        d2h_bytes = npx * 4 // world
+    else:
+        surf_host = torch.empty((H4K, W4K), dtype=torch.int32).pin_memory()
+        host_frame = surf_host.numpy().view(np.uint32)
+
+        def frame_e2e():
+            ctx.set_frame(fp)
+            ctx.rt_frame(host_frame)
+        call = "b2r_set_frame + b2r_rt_frame (pinned host surface)"
+        d2h_bytes = npx * 4
     for _ in range(max(args.warmup, 1)):
         frame_e2e()
     barrier()
@@ -275,22 +376,40 @@ def run_gpu_arm(args, pkg):
         frame_e2e()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e_value = world * rays * args.steps / e2e_s / 1e6
+        mine = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.broadcast(mine, src=0)  # rank 0's clock: its steps end when every rank has delivered
+        e2e_s = float(mine.item())
+    e2e_value = rays * args.steps / e2e_s / 1e6
     h2d_bytes = 1728 + 16 * (1 + fp.numLights)  # DevFrame up to and including the used ray origins (b2r_set_frame)
-    d2h_bytes = npx * 4
+    e2e_verified = None
+    barrier()
+    if rank == 0:
+        ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr())
+        ctx.synchronize()
+        e2e_verified = bool(np.array_equal(host_frame, d_surf.cpu().numpy().view(np.uint32)))
+    barrier()
+    if world > 1:
+        ctx.unpin_host_buffer(shm.frame)
+        host_frame = None
+        shm.close()
 
-    extra = {"frames_per_s": world * args.steps / (total_ms * 1e-3), "rays_per_frame": rays,
-             "algorithmic_gflop_per_frame": flops / 1e9, "e2e_frames_per_s": world * args.steps / e2e_s}
+    extra = {"frames_per_s": args.steps / (total_ms * 1e-3), "rays_per_frame": rays,
+             "algorithmic_gflop_per_frame": flops / 1e9, "e2e_frames_per_s": args.steps / e2e_s,
+             "split_verified": split_verified, "e2e_frame_verified": e2e_verified}
+
+    # weak scaling for comparison: every rank draws its own frames (nothing exchanged), with pixelColours as in round 1
+    def frame_own():
+        ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr(), d_col.data_ptr())
+    own_ms = allmax(timed_loop(frame_own, max(args.steps // 2, 5), args.warmup)) / max(args.steps // 2, 5)
+    extra["frames_per_rank_weak"] = {"ms_per_frame": own_ms, "value": world * rays / (own_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                                     "scaling": "weak", "outputs": "pixelColours + 32-bit surface in HBM, one frame per rank"}
 
     # BASELINE config 5: 360-frame camera orbit, frames partitioned across the ranks (no collective on the data path);
     # every frame re-uploads its camera (b2r_set_frame) and is traced + resolved at 4K, 1 spp + hard shadow
-    par = pkg.parallel
     fp_orbit = pkg.default_frame_params(0, W4K, H4K)
     my_frames = par.frames_for_rank(rank, world, 360)
+
     def orbit_pass():
         for fidx in my_frames:
             pos, rot = pkg.orbit_camera(fidx, 360)
@@ -302,50 +421,73 @@ def run_gpu_arm(args, pkg):
     t0 = time.perf_counter()
     orbit_pass()
     barrier()
-    orbit_s = time.perf_counter() - t0
-    t = torch.tensor([orbit_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    orbit_s = float(t.item())
+    orbit_s = allmax(time.perf_counter() - t0)
     extra["orbit_360_frames_4k_1spp"] = {"seconds": orbit_s, "frames_per_s": 360 / orbit_s,
                                          "partition": f"frames f = rank (mod {world})", "timing": "wall clock incl. per-frame b2r_set_frame"}
     ctx.set_frame(fp)
+    # ... and end to end: every frame through the host ABI to a 24-bit BMP file (what the reference's SDL_SaveBMP
+    # leaves, raytracer.cpp:175): BGR conversion on the GPU, 3 bytes per pixel over PCIe, files written by host
+    # threads (b2r_group_rt_frames, one group member per rank)
+    try:
+        import glob
+        sv = os.statvfs("/dev/shm")
+        free_gb = sv.f_bavail * sv.f_frsize / 1e9
+        nfr = 360 if free_gb > 16 else 96
+        frames = []
+        for fidx in range(rank, nfr, world):
+            f = pkg.default_frame_params(0, W4K, H4K)
+            pos, rot = pkg.orbit_camera(fidx, 360)
+            f.set_camera(pos, rot, H4K / 2)
+            frames.append(f)
+        grp = pkg.Group(W4K, H4K, [local])
+        grp.set_triangles(tris)
+        pattern = f"/dev/shm/b2r_orbit_{os.environ.get('MASTER_PORT', '0')}_{rank}_%04d.bmp"
+        grp.rt_frames(frames[:2], bmp_pattern=pattern)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        grp.rt_frames(frames, bmp_pattern=pattern)
+        barrier()
+        bmp_s = allmax(time.perf_counter() - t0)
+        nbytes = sum(os.path.getsize(p) for p in glob.glob(pattern.replace("%04d", "*")))
+        for pth in glob.glob(pattern.replace("%04d", "*")):
+            os.unlink(pth)
+        grp.close()
+        extra["orbit_360_frames_4k_e2e_with_bmp"] = {
+            "frames": nfr, "seconds": bmp_s, "frames_per_s": nfr / bmp_s, "bmp_bytes_written_this_rank": nbytes,
+            "path": "/dev/shm (files removed afterwards)",
+            "call": "b2r_group_rt_frames(bmp_pattern): b2r_set_frame + trace + BGR24 on the GPU + D2H + b2r_write_bmp on host threads"}
+    except Exception as ex:  # a full /dev/shm must not cost the headline
+        extra["orbit_360_frames_4k_e2e_with_bmp"] = {"error": repr(ex)}
+    barrier()
 
-    # single-frame row-band split + NCCL all-gather of the surface bands (strong scaling, N > 1 only)
     if world > 1 and H4K % world == 0:
+        # the other exchange forms, for comparison (strong scaling, same frame)
         band = H4K // world
         y0, y1 = rank * band, (rank + 1) * band
+
         def frame_band():
             ctx.rt_frame_device_async(y0, y1, d_surf.data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(d_surf.view(-1), d_surf.view(-1)[y0 * W4K:y1 * W4K])
-        bms = timed_loop(frame_band, args.steps, args.warmup)
-        t = torch.tensor([bms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        bms = float(t.item()) / args.steps
-        extra["band_split"] = {"ms_per_frame": bms, "value": rays / (bms * 1e-3) / 1e6, "unit": "Mrays/s",
-                               "scaling": "strong", "collective": "nccl all_gather of 32-bit surface bands"}
-        # fused variant: the trace kernel stores each resolved pixel straight into every rank's surface over NVLink
-        # (peer-mapped buffers) and the ranks take interleaved tile rows, so the exchange is part of the one kernel
-        # and the load is even; a 4-byte all-reduce orders the frames
+        bms = allmax(timed_loop(frame_band, args.steps, args.warmup)) / args.steps
+        extra["band_split_nccl_allgather"] = {"ms_per_frame": bms, "value": rays / (bms * 1e-3) / 1e6, "unit": "Mrays/s",
+                                              "scaling": "strong", "collective": "contiguous row bands + nccl all_gather of 32-bit surface bands"}
+        # all-gather inside the trace kernel: every rank stores its pixels into every rank's surface (round 1's form)
         mine, handle = ctx.shared_alloc(npx * 4)
         handles = [None] * world
         dist.all_gather_object(handles, handle)
         ptrs = [mine if r == rank else ctx.shared_open(handles[r]) for r in range(world)]
         tick = torch.zeros(1, dtype=torch.int32, device=dev)
         order = [mine] + [p for r, p in enumerate(ptrs) if r != rank]
+
         def frame_band_fused():
-            # ONE kernel per rank: traces its interleaved tile rows and stores every pixel into all ranks' surfaces
             ctx.rt_frame_split_device_async(rank, world, order)
             with torch.cuda.stream(stream):
                 dist.all_reduce(tick)
-        fms = timed_loop(frame_band_fused, args.steps, args.warmup)
-        t = torch.tensor([fms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fms = float(t.item()) / args.steps
-        extra["band_split_fused"] = {"ms_per_frame": fms, "value": rays / (fms * 1e-3) / 1e6, "unit": "Mrays/s",
-                                     "scaling": "strong",
-                                     "exchange": "trace kernel stores into peer-mapped surfaces (CUDA IPC over NVLink), tile rows interleaved across ranks"}
+        fms = allmax(timed_loop(frame_band_fused, args.steps, args.warmup)) / args.steps
+        extra["split_allgather_in_kernel"] = {"ms_per_frame": fms, "value": rays / (fms * 1e-3) / 1e6, "unit": "Mrays/s",
+                                              "scaling": "strong",
+                                              "exchange": "trace kernel stores into every rank's peer-mapped surface + a 4-byte nccl all-reduce per frame"}
         # rasteriser config 4, sort-first: the 1,004,670 triangles are replicated, every rank rasterises and shades
         # its row band and the shade kernel's surface rows are gathered with NCCL.  Per-triangle work (vertex
         # shading, classification) is not divided by the band, so this split is bounded by it.
@@ -354,14 +496,13 @@ def run_gpu_arm(args, pkg):
         rctx.set_triangles(pkg.tessellate(tris, 183))
         rctx.set_frame(pkg.default_frame_params(1, W4K, H4K))
         rctx.ras_cull()
+
         def ras_band():
             rctx.ras_frame_device_async(y0, y1, d_surf.data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(d_surf.view(-1), d_surf.view(-1)[y0 * W4K:y1 * W4K])
-        rms = timed_loop(ras_band, max(args.steps // 4, 5), args.warmup)
-        t = torch.tensor([rms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rms = float(t.item()) / max(args.steps // 4, 5)
+        nr = max(args.steps // 4, 5)
+        rms = allmax(timed_loop(ras_band, nr, args.warmup)) / nr
         extra["ras_band_split_4k_1m_tris"] = {"ms_per_frame": rms, "frames_per_s": 1e3 / rms, "scaling": "strong",
                                               "collective": "nccl all_gather of 32-bit surface bands"}
         rctx.close()
@@ -372,31 +513,55 @@ def run_gpu_arm(args, pkg):
         barrier()
         ctx.shared_free(mine)
 
+    barrier()
+    if world > 1 and rank != 0:
+        ctx.shared_close(root)
+    barrier()
     if rank == 0:
-        extra.update(other_configs(pkg, torch, dev, stream, flush, local, cpu=(world == 1 and not args.no_cpu)))
+        ctx.shared_free(root_mem)
+
+    if rank == 0:
+        others = other_configs(pkg, torch, dev, stream, flush, local, cpu=(world == 1 and not args.no_cpu))
+        ras_roof = others.pop("roofline_rasteriser", None)
+        extra.update(others)
         cpu = cpu_reference_sample(pkg, row_step=4, steps=3, warmup=1) if world == 1 and not args.no_cpu else None
+        roofline = {
+            "bound": "fp32", "achieved": exec_tf, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (exec_tf / peak_tf) if (exec_tf and peak_tf) else None,
+            "traffic": execp.get("dram_bytes_per_launch"),
+            "kernel": "rt_trace_shade_kernel", "kernel_ms": kern_ms,
+            "executed_fp32_flops_per_launch": exec_flops,
+            "issue_slot_frac": execp.get("issue_slot_frac"), "fma_pipe_frac": execp.get("fma_pipe_frac"),
+            "source": "profiles/r02_rt_trace_exec.json (ncu: smsp__sass_thread_inst_executed_op_{fadd,fmul,ffma}_pred_on, "
+                      "ffma = 2 flops; per launch of this exact workload) / kernel time measured in this run",
+            "algorithmic_speedup_vs_bruteforce": algo_tf / peak_tf if peak_tf else None,
+            "algorithmic_tflops_bruteforce_model": algo_tf,
+            "exact_tests_frac": st["exact_tests"] / float(rays * len(tris)),
+            "note": "frac = executed FP32 flops / time / measured FFMA peak, <= 1 by construction (exact-order mul+add code "
+                    "cannot use FMA, so 0.5 would already saturate the pipe). algorithmic_speedup_vs_bruteforce is round 1's "
+                    "number: SURVEY 8d flops of the brute-force formulation / time / peak; the conservative culling leaves "
+                    "exact_tests_frac of those tests to execute.",
+            "peak_source": "FFMA microbenchmark measured in this run (b2r_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry"}
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "parallelism": f"frames x{world}",
-                       "l2": "flushed between steps (256 MB fill)", "outputs": "pixelColours + 32-bit surface in HBM"},
+            "config": {"workload": WORKLOAD, "frames_per_step": 1,
+                       "parallelism": f"one frame split over {world} GPU(s): interleaved 8-row tile rows, gathered on rank 0 over NVLink"
+                                      if world > 1 else "one frame on one GPU",
+                       "l2": "flushed between steps (256 MB fill)", "outputs": "32-bit surface in HBM (on rank 0's GPU)",
+                       "split_verified": split_verified},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "call": "b2r_set_frame + b2r_rt_frame (pinned host surface)"},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.steps * 1e3, "call": call,
+                    "frame_verified": e2e_verified},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                         "kernel": "rt_trace_shade_kernel", "kernel_ms": kern_ms,
-                         "exact_tests_frac": st["exact_tests"] / float(rays * len(tris)),
-                         "note": "achieved = SURVEY 8d algorithmic flops (every ray x every triangle) / kernel time; "
-                                 "conservative culling leaves only exact_tests_frac of those tests to execute, so "
-                                 "frac can exceed 1 -- profiles/ has the executed-instruction view (issue slots)",
-                         "peak_source": "FFMA microbenchmark measured in this run (b2r_measure_fp32_peak); "
-                                        "MEASURED_PEAKS.json has no FP32 entry"},
+            "roofline": roofline,
             "clocks": clocks,
             "extra": extra,
         }
+        if ras_roof:
+            line["roofline_rasteriser"] = ras_roof
         if cpu:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         sys.stdout.flush()
@@ -492,10 +657,23 @@ def other_configs(pkg, torch, dev, stream, flush, local, cpu=False):
         pass
     src = "MEASURED_PEAKS.json hbm_gbs" if peak else "fallback 6650 GB/s (B200_PROFILING.md)"
     peak = peak or 6650.0
-    out["ras_4k_1m_tris"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "triangles": len(big),
-                             "roofline": {"bound": "hbm", "achieved": abytes / ms / 1e6, "peak": peak, "unit": "GB/s",
-                                          "frac": abytes / ms / 1e6 / peak, "algorithmic_bytes": abytes,
-                                          "peak_source": src, "scope": "whole Draw() pipeline, all kernels"}}
+    prof = _load_json("r02_ras_traffic.json") or {}
+    out["roofline_rasteriser"] = {"bound": "hbm", "achieved": abytes / ms / 1e6, "peak": peak, "unit": "GB/s",
+                                  "frac": abytes / ms / 1e6 / peak, "traffic": prof.get("sortlast_dram_bytes_per_frame"),
+                                  "algorithmic_bytes": abytes, "ms_per_frame": ms, "triangles": len(big),
+                                  "workload": "rasteriser, tessellated Cornell box (1,004,670 triangles) 3840x2160, depth + colour out",
+                                  "pipeline": "sort-last (default): ras_small + ras_shade",
+                                  "peak_source": src, "scope": "whole Draw() pipeline, all kernels",
+                                  "traffic_source": "profiles/r02_ras_traffic.json (ncu dram__bytes_read+write, summed over the frame's kernels)"}
+    out["ras_4k_1m_tris"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "triangles": len(big)}
+    # the screen-tile pipeline on the same frame (B2R_OPT_RAS_VARIANT = 2)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, 2)
+    ms2 = avg_ms(lambda: ctx.ras_draw_device_async(0, H4K, dep.data_ptr(), col.data_ptr()))
+    out["ras_4k_1m_tris_tiled"] = {"ms_per_frame": ms2, "frames_per_s": 1e3 / ms2,
+                                   "roofline": {"bound": "hbm", "achieved": abytes / ms2 / 1e6, "peak": peak, "unit": "GB/s",
+                                                "frac": abytes / ms2 / 1e6 / peak, "traffic": prof.get("tiles_dram_bytes_per_frame")},
+                                   "pipeline": "screen tiles: ras_setup + ras_bin + ras_tile (keys and spans in shared memory)"}
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, 0)
     ctx.close()
     if cpu:
         out["cpu_reference"] = cpu_reference_other_configs(pkg, big)

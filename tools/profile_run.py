@@ -19,6 +19,16 @@ if which == "rt":
     for _ in range(3):
         ctx.rt_frame_device_async(0, H, surf.data_ptr(), col.data_ptr())
     ctx.synchronize()
+elif which == "rtsurf":  # the bench's step at N = 1: surface only
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    fp = pkg.default_frame_params(0, W, H)
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    ctx.set_frame(fp)
+    surf = torch.empty((H, W), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ctx.rt_frame_device_async(0, H, surf.data_ptr())
+    ctx.synchronize()
 elif which == "dof":
     ctx = pkg.Context(W, H)
     ctx.set_triangles(tris)
@@ -42,9 +52,10 @@ elif which == "ras30":
     for _ in range(3):
         ctx.ras_draw_device_async(0, H, dep.data_ptr(), col.data_ptr())
     ctx.synchronize()
-else:
+else:  # "ras" (sort-last, default) or "rastiles" (B2R_OPT_RAS_VARIANT = 2)
     big = pkg.tessellate(tris, 183)
     ctx = pkg.Context(W, H)
+    ctx.set_option(pkg.capi.OPT_RAS_VARIANT, 2 if which == "rastiles" else 0)
     ctx.set_triangles(big)
     ctx.set_frame(pkg.default_frame_params(1, W, H))
     ctx.ras_cull()
