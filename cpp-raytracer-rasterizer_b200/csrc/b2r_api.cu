@@ -378,6 +378,26 @@ struct RtSplit {
     unsigned* arrive = nullptr;  // incremented once when the launch's pixels have landed (gather to a root)
 };
 
+// stream memory operations: cuStreamWaitValue32 through the runtime's loader (absent on some driver set-ups)
+static int probe_mem_ops(Ctx* c) {
+    if (c->memOpsProbed) return B2R_OK;
+    c->memOpsProbed = true;
+    cudaDriverEntryPointQueryResult qr;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess && fn)
+        c->waitValue32 = fn;
+    cudaGetLastError();
+    return B2R_OK;
+}
+
+static int ensure_copy_stream(Ctx* c) {
+    if (c->copyStream) return B2R_OK;
+    CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking), "cudaStreamCreate (copy)");
+    for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->partDone[i], cudaEventDisableTiming), "cudaEventCreate");
+    return B2R_OK;
+}
+
 static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
                           uint32_t* d_surf = nullptr, int bandTileRows = 0, const RtSplit* split = nullptr) {
     c->lastDraw = 0;
@@ -466,20 +486,10 @@ static int rt_draw_host(Ctx* c, int y0, int y1, float* col, b2r_intersection* cl
     const bool anyOut = surface || col || clo || foc;
     // the depth-of-field window reads rows of neighbouring sub-bands, so it resolves only after the whole draw
     int parts = (!anyOut || (surface && c->params.dofEnabled)) ? 1 : (rows >= 1024 ? 4 : (rows >= 256 ? 2 : 1));
-    if (parts > 1 && !c->copyStream) {
-        CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking), "cudaStreamCreate (copy)");
-        for (int i = 0; i < 4; ++i) CU(cudaEventCreateWithFlags(&c->partDone[i], cudaEventDisableTiming), "cudaEventCreate");
-    }
+    if (parts > 1)
+        if (int rc = ensure_copy_stream(c)) return rc;
     cudaStream_t drawStream = c->stream;
-    if (parts > 1 && !c->memOpsProbed) {  // stream memory operations: cuStreamWaitValue32 through the runtime's loader
-        c->memOpsProbed = true;
-        cudaDriverEntryPointQueryResult qr;
-        void* fn = nullptr;
-        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess && fn)
-            c->waitValue32 = fn;
-        cudaGetLastError();
-    }
+    if (parts > 1) probe_mem_ops(c);
     if (parts > 1 && c->waitValue32 && c->optRtVariant != 4) {
         // One launch for the whole band.  The kernel counts finished warp tiles per sub-band (tiles are handed out
         // in row order); the copy stream waits -- on the GPU, no host involvement -- until a sub-band's count is
@@ -622,15 +632,7 @@ int b2r_stream_wait_value32(b2r_ctx* ctx, const uint32_t* d_word, uint32_t value
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (int rc = bind(c)) return rc;
     if (!d_word) return fail(c, B2R_E_INVALID, "stream_wait_value32: null word");
-    if (!c->memOpsProbed) {  // stream memory operations: cuStreamWaitValue32 through the runtime's loader
-        c->memOpsProbed = true;
-        cudaDriverEntryPointQueryResult qr;
-        void* fn = nullptr;
-        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess && fn)
-            c->waitValue32 = fn;
-        cudaGetLastError();
-    }
+    probe_mem_ops(c);
     if (!c->waitValue32) return fail(c, B2R_E_UNSUPPORTED, "stream memory operations (cuStreamWaitValue32) are not available");
     typedef int (*WaitFn)(cudaStream_t, unsigned long long, unsigned, unsigned);
     if (reinterpret_cast<WaitFn>(c->waitValue32)(c->stream, (unsigned long long)(uintptr_t)d_word, value, 0u /* GEQ */) != 0)
@@ -661,22 +663,58 @@ int b2r_rt_frame_part_async(b2r_ctx* ctx, int part, int nparts, uint32_t* surfac
     RtSplit sp;
     sp.stride = nparts;
     sp.offset = part;
-    if (int rc = rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, c->surface.as<uint32_t>(), 0, &sp)) return rc;
-    // rows of tile row t: [8t, 8t+8); this part owns t = part, part + nparts, ...: a 2-D copy with pitch nparts * 8 rows
-    const int tileRows = (c->H + 7) / 8;
+    // rows of tile row t: [8t, 8t+8); this part owns t = part, part + nparts, ...: 2-D copies with pitch nparts * 8 rows
+    const int tileRows = (c->H + 7) / 8, tilesX = (c->W + 31) / 32;
     const int mine = tileRows > part ? (tileRows - part + nparts - 1) / nparts : 0;
-    if (mine == 0) return B2R_OK;
-    const size_t rowBytes = (size_t)c->W * 4, chunk = 8 * rowBytes, pitch = (size_t)nparts * chunk, first = (size_t)part * chunk;
-    const int lastTile = part + (mine - 1) * nparts;
-    const int lastRows = std::min(8, c->H - lastTile * 8);  // the frame's last tile row may be short
-    const int full = lastRows == 8 ? mine : mine - 1;
-    if (full > 0)
-        CU(cudaMemcpy2DAsync((char*)surface + first, pitch, (const char*)c->surface.p + first, pitch, chunk, (size_t)full,
-                             cudaMemcpyDeviceToHost, c->stream), "D2H copy (tile rows)");
-    if (full < mine) {
-        const size_t off = (size_t)lastTile * chunk;
-        CU(cudaMemcpyAsync((char*)surface + off, (const char*)c->surface.p + off, (size_t)lastRows * rowBytes,
-                           cudaMemcpyDeviceToHost, c->stream), "D2H copy (last tile row)");
+    const size_t rowBytes = (size_t)c->W * 4, chunk = 8 * rowBytes, pitch = (size_t)nparts * chunk;
+    // local tile rows [t0,t1) of this part -> host, on stream s
+    auto copy_tile_rows = [&](int t0, int t1, cudaStream_t s) -> cudaError_t {
+        if (t1 <= t0) return cudaSuccess;
+        const int lastTile = part + (t1 - 1) * nparts;
+        const int lastRows = std::min(8, c->H - lastTile * 8);  // the frame's last tile row may be short
+        const int full = lastRows == 8 ? t1 - t0 : t1 - t0 - 1;
+        const size_t first = (size_t)(part + t0 * nparts) * chunk;
+        cudaError_t e = cudaSuccess;
+        if (full > 0)
+            e = cudaMemcpy2DAsync((char*)surface + first, pitch, (const char*)c->surface.p + first, pitch, chunk, (size_t)full,
+                                  cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess && full < t1 - t0) {
+            const size_t off = (size_t)lastTile * chunk;
+            e = cudaMemcpyAsync((char*)surface + off, (const char*)c->surface.p + off, (size_t)lastRows * rowBytes,
+                                cudaMemcpyDeviceToHost, s);
+        }
+        return e;
+    };
+    if (int rc = probe_mem_ops(c)) return rc;
+    if (mine >= 16 && c->waitValue32 && c->optRtVariant != 4) {
+        // As in b2r_rt_frame: one launch; the kernel counts finished warp tiles per sub-band of its own tile rows and a
+        // second stream copies a sub-band out as soon as its count is complete, while the rest is still being traced.
+        if (int rc = ensure_copy_stream(c)) return rc;
+        typedef int (*WaitFn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+        const int perBand = (mine + 7) / 8, nb = (mine + perBand - 1) / perBand;
+        if (!c->rtSched.p) {
+            CU(c->rtSched.reserve(64 + 4 * kMaxCopyBands), "scheduler alloc");
+            CU(cudaMemsetAsync(c->rtSched.p, 0, 64 + 4 * kMaxCopyBands, c->stream), "scheduler clear");
+        }
+        unsigned* done = c->rtSched.as<unsigned>() + 16;
+        CU(cudaMemsetAsync(done, 0, 4 * kMaxCopyBands, c->stream), "band counters clear");
+        CU(cudaEventRecord(c->partDone[0], c->stream), "cudaEventRecord");
+        CU(cudaStreamWaitEvent(c->copyStream, c->partDone[0], 0), "cudaStreamWaitEvent");
+        if (int rc = rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, c->surface.as<uint32_t>(), perBand, &sp)) return rc;
+        for (int b = 0; b < nb; ++b) {
+            const int t0 = b * perBand, t1 = std::min(mine, (b + 1) * perBand);
+            const unsigned want = (unsigned)(t1 - t0) * (unsigned)tilesX * 8u;
+            if (reinterpret_cast<WaitFn>(c->waitValue32)(c->copyStream, (unsigned long long)(uintptr_t)(done + b), want,
+                                                         0u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+                return fail(c, B2R_E_CUDA, "cuStreamWaitValue32 failed");
+            CU(copy_tile_rows(t0, t1, c->copyStream), "D2H copy (tile rows)");
+        }
+        // the context's stream completes after the copies: b2r_synchronize covers both
+        CU(cudaEventRecord(c->partDone[1], c->copyStream), "cudaEventRecord");
+        CU(cudaStreamWaitEvent(c->stream, c->partDone[1], 0), "cudaStreamWaitEvent");
+    } else {
+        if (int rc = rt_launch_band(c, 0, c->H, nullptr, nullptr, nullptr, c->surface.as<uint32_t>(), 0, &sp)) return rc;
+        CU(copy_tile_rows(0, mine, c->stream), "D2H copy (tile rows)");
     }
     c->surfaceValid = false;
     return B2R_OK;

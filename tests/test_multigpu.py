@@ -11,15 +11,15 @@ from util import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_band_exchange_and_frame_partition_two_gpus():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_band_exchange_and_frame_partition(world):
     import torch
     n = torch.cuda.device_count()
-    if n < 2:
-        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    world = 2
+    if n < world:
+        pytest.skip(f"needs {world} GPUs (run with gpurun --gpus {world})")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + world),
                           os.path.join(ROOT, "tests", "multigpu_band_worker.py")], env=env, capture_output=True, text=True,
                          timeout=600)
     assert out.returncode == 0 and "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
