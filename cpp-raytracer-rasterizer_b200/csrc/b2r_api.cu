@@ -691,7 +691,9 @@ int b2r_rt_frame_part_async(b2r_ctx* ctx, int part, int nparts, uint32_t* surfac
         // second stream copies a sub-band out as soon as its count is complete, while the rest is still being traced.
         if (int rc = ensure_copy_stream(c)) return rc;
         typedef int (*WaitFn)(cudaStream_t, unsigned long long, unsigned, unsigned);
-        const int perBand = (mine + 7) / 8, nb = (mine + perBand - 1) / perBand;
+        // a sub-band per ~16 tile rows, at most 8: every one costs a stream wait and a copy call on the host
+        const int wantBands = std::max(1, std::min(8, mine / 16));
+        const int perBand = (mine + wantBands - 1) / wantBands, nb = (mine + perBand - 1) / perBand;
         if (!c->rtSched.p) {
             CU(c->rtSched.reserve(64 + 4 * kMaxCopyBands), "scheduler alloc");
             CU(cudaMemsetAsync(c->rtSched.p, 0, 64 + 4 * kMaxCopyBands, c->stream), "scheduler clear");

@@ -37,6 +37,8 @@
 // (tests/test_rt_parity.py checks this).
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "b2r_internal.h"
 #include "exact.cuh"
 #include "pixel_pack.cuh"
@@ -837,6 +839,10 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
         c->rtKernelCache.push_back({(const void*)kern, smem, perSM});
     }
     int grid = c->smCount * perSM;
+    if (const char* env = getenv("B2R_RT_CTAS_PER_SM")) {  // diagnostic override
+        const int v = atoi(env);
+        if (v >= 1 && v <= perSM) grid = c->smCount * v;
+    }
     if (grid > a.numTiles) grid = a.numTiles;
     if (grid < 1) {  // nothing to draw: the root still hears from this part
         if (a.arrive) {
@@ -850,7 +856,9 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
     RtLaunch b = a;
     const int work = a.fr.aaN * a.fr.aaN * a.fr.nOrigins;
     int batch = work >= 8 ? 1 : (work >= 4 ? 2 : 4);
-    if ((long long)a.numTiles < 8LL * grid) batch = 0;
+    // ... unless a tile is heavy (16+ rays per pixel): one part of a frame split over 8 GPUs has ~7 tiles per warp, and
+    // strided static assignment left some SMs busy 1.7x as long as others (220 -> 188 us for an eighth of config 3)
+    if ((long long)a.numTiles < 8LL * grid && work < 16) batch = 0;
     b.batch = batch;
     kern<<<grid, kThreads, smem, s>>>(b);
     c->launches++;

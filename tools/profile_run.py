@@ -29,6 +29,17 @@ elif which == "rtsurf":  # the bench's step at N = 1: surface only
     for _ in range(3):
         ctx.rt_frame_device_async(0, H, surf.data_ptr())
     ctx.synchronize()
+elif which.startswith("rtpart"):  # one part of the frame split N ways (gather form, local surface): kernel time vs 1/N
+    n = int(which[6:])
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    fp = pkg.default_frame_params(0, W, H)
+    fp.aaEnabled, fp.aaSamples = 1, 4
+    ctx.set_frame(fp)
+    surf = torch.zeros((H * W + 64,), dtype=torch.int32, device=dev)
+    for part in (0, 0, 1, n - 1):
+        ctx.rt_frame_gather_device_async(part, n, surf.data_ptr(), surf.data_ptr() + H * W * 4)
+    ctx.synchronize()
 elif which == "dof":
     ctx = pkg.Context(W, H)
     ctx.set_triangles(tris)
