@@ -166,9 +166,53 @@ def kat_500():
     json.dump(k, open(os.path.join(HERE, "kat_500x500.json"), "w"), indent=1, sort_keys=True)
 
 
+def kat_4k():
+    """Digests of the BASELINE configurations at the size bench.py quotes them (3840x2160), from the reference itself:
+    config 3 (AA 4x4), config 3b (16 jittered light samples), three frames of the config-5 orbit, config 4 (1,004,670
+    triangles).  The GPU test compares digests only, so no CPU run is needed on the GPU box."""
+    w, h = 3840, 2160
+    k = {}
+    rt = RefRaytracer(w, h)
+    rt.load_test_model()
+    table = rt.add_light_reference(1, True, [0, -0.5, -0.7], [1, 1, 1], 14.0)
+    names = ("pixelColours", "focalDistances", "closest", "surface")
+    rt.set_lights(LIGHT, table)
+    rt.set_camera_yaw([0, 0, -2], 0.0, h / 2.0)
+    rt.set_flags(aa=True, aa_samples=4)
+    r = rt.draw()
+    k["config3_aa4x4"] = {"sha256": {n: sha(r[n]) for n in names},
+                          "hit_pixels": int((r["closest"]["triangleIndex"] >= 0).sum())}
+    rt.set_flags(soft=True, soft_samples=16)
+    r = rt.draw()
+    k["config3b_soft16"] = {"sha256": {n: sha(r[n]) for n in names}, "jitter_table_sha256": sha(table)}
+    rt.set_flags()
+    k["config5_orbit"] = {}
+    for f in (45, 170, 300):
+        pos, rot = pkg.orbit_camera(f, 360)
+        rt.set_camera(pos, rot, h / 2.0)
+        r = rt.draw()
+        k["config5_orbit"][str(f)] = {"sha256": {n: sha(r[n]) for n in names}}
+    del rt
+    ra = RefRasteriser(w, h)
+    big = pkg.tessellate(pkg.cornell_box(), 183)
+    ra.set_triangles(big)
+    ra.set_lights(LIGHT)
+    ra.set_flags()
+    _, culled, _ = ra.update_yaw([0, 0, -3], 0.0, float(h))
+    r = ra.draw()
+    k["config4_ras_1m"] = {"triangles": int(len(big)), "culled": int(culled.sum()), "culled_sha256": sha(culled.astype(np.uint8)),
+                           "covered": int((r["winner"] >= 0).sum()), "depth_tests": int(r["depth_tests"]),
+                           "sha256": {n: sha(r[n]) for n in ("depthBuffer", "pixelColours", "focalDistances", "winner", "surface")}}
+    json.dump(k, open(os.path.join(HERE, "kat_3840x2160.json"), "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "kat4k":
+        kat_4k()
+        sys.exit(0)
     rt_frames()
     ras_frames()
     substage_vectors()
     kat_500()
+    kat_4k()
     print("golden fixtures written to", HERE)
