@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "lib", "libb2r.so")
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(PKG_DIR, "lib", "libb2r.so")  # B2R_LIB: e.g. the bounds-checking debug build
 
 MAX_LIGHTS = 32
 RANDOM_POSITIONS = 256

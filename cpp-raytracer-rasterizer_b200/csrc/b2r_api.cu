@@ -401,6 +401,7 @@ static int ensure_copy_stream(Ctx* c) {
 static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection* d_clo, float* d_foc,
                           uint32_t* d_surf = nullptr, int bandTileRows = 0, const RtSplit* split = nullptr) {
     c->lastDraw = 0;
+    c->coloursValid = c->surfaceValid = false;  // set again by the host-buffer draws once their frame is complete
     if (y1 == y0) return B2R_OK;
     RtLaunch a;
     a.geom = c->geom.as<float4>();
@@ -732,6 +733,7 @@ int b2r_rt_frame(b2r_ctx* ctx, uint32_t* surface, float* col, b2r_intersection* 
 static int ras_launch_band(Ctx* c, int y0, int y1, float* d_dep, float* d_col, float* d_foc, int32_t* d_win,
                            uint32_t* d_surf) {
     c->lastDraw = 1;
+    c->coloursValid = c->surfaceValid = false;  // set again by the host-buffer draws once their frame is complete
     if (y1 == y0) return B2R_OK;
     RasLaunch a;
     a.raw = c->stride == 64 ? c->raw.as<unsigned char>() : c->raw64.as<unsigned char>();
@@ -966,7 +968,9 @@ int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface) {
     if (int rc = bind(c)) return rc;
     if (!surface) return fail(c, B2R_E_INVALID, "null surface");
     const bool haveSurface = c->surfaceValid && !c->coloursValid;  // fused raytracer frame: already resolved
-    if (c->lastDraw < 0 || (!haveSurface && !c->colours.p)) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    if (c->lastDraw < 0 || (!haveSurface && !c->coloursValid))
+        return fail(c, B2R_E_NO_SCENE, "resolve: the last draw on this context left no frame here (it was a device-pointer "
+                                       "draw, a partial band without pixelColours, or there was none)");
     if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
     const size_t n = (size_t)c->W * c->H;
     CU(c->surface.reserve(n * 4), "alloc surface");
@@ -988,7 +992,9 @@ int b2r_resolve_bgr8(b2r_ctx* ctx, uint8_t* bgr) {
     if (int rc = bind(c)) return rc;
     if (!bgr) return fail(c, B2R_E_INVALID, "null bgr");
     const bool haveSurface = c->surfaceValid && !c->coloursValid;  // fused raytracer frame: already resolved
-    if (c->lastDraw < 0 || (!haveSurface && !c->colours.p)) return fail(c, B2R_E_NO_SCENE, "resolve before any draw");
+    if (c->lastDraw < 0 || (!haveSurface && !c->coloursValid))
+        return fail(c, B2R_E_NO_SCENE, "resolve: the last draw on this context left no frame here (it was a device-pointer "
+                                       "draw, a partial band without pixelColours, or there was none)");
     if (c->params.dofEnabled && !c->focal.p) return fail(c, B2R_E_INVALID, "resolve: the last draw did not produce focalDistances");
     const size_t n = (size_t)c->W * c->H, payload = b2r_bmp_payload_bytes(c->W, c->H);
     CU(c->surface.reserve(n * 4), "alloc surface");

@@ -8,6 +8,23 @@
 
 #include "../../include/b2r.h"
 
+// Debug build (nvcc -DB2R_DEBUG_BOUNDS, __graft_entry__.build_debug(): libb2r_dbg.so): every index into a scheduler
+// word, band counter, per-warp list, row-record slot or tile array is checked; a violation prints the site and traps,
+// which the host sees as a CUDA error.  compute-sanitizer is not available on the GPU pool, so the randomised soak is
+// run once per round against this build instead (profiles/r02_soak_debug_bounds.log).  Release builds: no code.
+#ifdef B2R_DEBUG_BOUNDS
+#include <stdio.h>
+#define B2R_BOUND(i, n)                                                                                          \
+    do {                                                                                                         \
+        if (!((unsigned long long)(long long)(i) < (unsigned long long)(long long)(n))) {                        \
+            printf("B2R_BOUND %s:%d: index %lld not in [0, %lld)\n", __FILE__, __LINE__, (long long)(i), (long long)(n)); \
+            __trap();                                                                                            \
+        }                                                                                                        \
+    } while (0)
+#else
+#define B2R_BOUND(i, n) ((void)0)
+#endif
+
 namespace b2r {
 
 // ---------------------------------------------------------------------------
@@ -217,8 +234,8 @@ struct Ctx {
         bool valid = false;
         unsigned long long gen = 0;
         int y0 = 0, y1 = 0;
-        unsigned nBig = 0, bigSamples = 0, totalRefs = 0;
-    } rasSizes;
+        unsigned nBig = 0, bigRows = 0, bigSamples = 0, totalRefs = 0;
+    } rasSizes, rasSizesSL;  // screen-tile pipeline, sort-last pipeline
     // pinned staging for host-pointer entry points
     void* pinned = nullptr;
     size_t pinnedCap = 0;

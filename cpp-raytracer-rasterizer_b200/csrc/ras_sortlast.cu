@@ -281,11 +281,15 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
                         psy = xdiv_step(dpy, fdx.b);
                     }
                     {   // one full 32-byte sector per row with fragments, for the shade pass
+                        B2R_BOUND(small_row_slot((unsigned)i, minY + rr), (size_t)a.T * kSmallRows);
                         float4* rec = reinterpret_cast<float4*>(rowRec + small_row_slot((unsigned)i, minY + rr));
                         rec[0] = make_float4(__int_as_float(lx), 0.f, lpx, lpy);
                         rec[1] = make_float4(psx, psy, 0.f, 0.f);
                     }
                     unsigned long long* keyRow = keys + (size_t)(minY + rr - a.y0) * (size_t)a.W;
+                    B2R_BOUND(minY + rr - a.y0, a.y1 - a.y0);
+                    B2R_BOUND(lx + 1 + i0, a.W);
+                    B2R_BOUND(lx + i1, a.W);
                     for (int q = i0; q < i1; ++q) {
                         const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
                         if (zinv > 0.0f)                                    // :606 against a buffer cleared to 0 (:188)
@@ -747,13 +751,31 @@ cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s
         c->rasErrPending = true;  // checked by the caller's next synchronising call (ras_take_error)
         c->rasErrCtr = ctr;
     } else if (T > 0) {
-        // how many large triangles / rows / edge samples: 16 bytes back to size the big path
-        if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
-        host = *reinterpret_cast<RasCounters*>(c->pinned);
-        if (host.err) {
-            cudaMemsetAsync(&ctr->sticky, 0, sizeof(unsigned), s);  // reported right here
-            return cudaErrorInvalidValue;
+        // How many large triangles / rows / edge samples: 32 bytes back to size the big path -- once per (scene,
+        // culling flags, frame params, band).  The counts are a pure function of those, so later frames of the same
+        // state reuse them and the draw only enqueues.
+        Ctx::RasSizes& z = c->rasSizesSL;
+        if (!(z.valid && z.gen == c->rasGen && z.y0 == a.y0 && z.y1 == a.y1)) {
+            if ((e = cudaMemcpyAsync(c->pinned, ctr, sizeof(RasCounters), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+            host = *reinterpret_cast<RasCounters*>(c->pinned);
+            if (host.err) {
+                cudaMemsetAsync(&ctr->sticky, 0, sizeof(unsigned), s);  // reported right here
+                return cudaErrorInvalidValue;
+            }
+            z.valid = true;
+            z.gen = c->rasGen;
+            z.y0 = a.y0;
+            z.y1 = a.y1;
+            z.nBig = host.nBig;
+            z.bigRows = host.bigRows;
+            z.bigSamples = host.bigSamples;
+        } else {
+            host.nBig = z.nBig;
+            host.bigRows = z.bigRows;
+            host.bigSamples = z.bigSamples;
+            c->rasErrPending = true;  // cannot be set for a state that drew cleanly before; kept for symmetry
+            c->rasErrCtr = ctr;
         }
     }
     if (host.nBig > 0) {

@@ -322,6 +322,7 @@ __device__ __forceinline__ void bin_append(unsigned* __restrict__ cursor, const 
     unsigned base = 0;
     if (lane == leader) base = atomicAdd(&cursor[tile], (unsigned)__popc(peers));
     base = __shfl_sync(peers, base, leader);
+    B2R_BOUND(base + (unsigned)__popc(peers & ((1u << lane) - 1u)), tileOffset[tile + 1] - tileOffset[tile]);
     refs[tileOffset[tile] + base + (unsigned)__popc(peers & ((1u << lane) - 1u))] = entry;
 }
 
@@ -653,6 +654,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, 
                 }
                 if (fits) {
                     const int r0 = (int)(S.rowBase[tid] - base), r1 = (int)(S.rowBase[tid + 1] - base);
+                    B2R_BOUND(r1 - 1, kRoundRows);
                     for (int r = r0; r < r1; ++r) S.rowTri[r] = (unsigned short)tid;
                 }
                 // ---- W: Interpolate (:615-637) of the small triangles' edges, one (triangle, edge) per thread ----
@@ -707,6 +709,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, 
                     for (int k = kLo; k <= kHi; ++k, idx += stride) {
                         // int(current.x): the chain stays within coord_margin of the vertex range, which passed the
                         // +-2^24 limit, so the plain truncating conversion equals the x86 one
+                        B2R_BOUND(idx, 3 * kRoundRows);
                         S.samples[idx] = make_float4(__int_as_float(__float2int_rz(cx)), cz, cpx, cpy);
                         cx = xadd(cx, sx);
                         cz = xadd(cz, sz);
@@ -764,9 +767,12 @@ __global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, 
                             r.psy = xdiv_step(dpy, fdx.b);
                         }
                         r.tri = S.tri[j];
+                        B2R_BOUND(ri, kRoundRows);
                         S.rec[ri] = r;
                         const unsigned lo = ((kTriMask - (r.tri & kTriMask)) << kSlotBits) | (unsigned)ri;
                         unsigned long long* krow = S.key + ((y - Y0) * kTileW - X0 + lx + 1);  // pixel of fragment q: krow[q]
+                        B2R_BOUND((y - Y0) * kTileW - X0 + lx + 1 + i0, kTilePix);
+                        B2R_BOUND((y - Y0) * kTileW - X0 + lx + i1, kTilePix);
                         for (int q = i0; q < i1; ++q) {
                             const float zinv = xadd(lz, xmul(zstep, (float)q));  // :667
                             if (zinv > 0.0f)                                     // :606 against a buffer cleared to 0 (:188)
@@ -782,6 +788,7 @@ __global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, 
                     const unsigned lo = (unsigned)S.key[tid + kTileThreads * i];
                     if (lo != seenLo[i]) {
                         seenLo[i] = lo;
+                        B2R_BOUND(lo & ((1u << kSlotBits) - 1u), kRoundRows);
                         const RowRec* r = &S.rec[lo & ((1u << kSlotBits) - 1u)];
                         const float fi = (float)(X0 + lane - r->lx - 1);
                         posx[i] = xadd(r->lpx, xmul(r->psx, fi));

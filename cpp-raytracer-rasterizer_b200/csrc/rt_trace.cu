@@ -483,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
             if (!a.bandDone) return;
             __threadfence();
             __syncwarp();
+            B2R_BOUND(ty / a.bandTileRows, 32);  // kMaxCopyBands
             if (lane == 0) atomicAdd(a.bandDone + ty / a.bandTileRows, 1u);
         };
         if (!__any_sync(kFull, inside)) {
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                     tile0 = m;
                     nList = 1;
                 } else if (m) {  // m is warp-uniform (a ballot)
+                    B2R_BOUND(nList, nChunks);
                     if (lane == 0) myTileList[nList] = make_uint2((unsigned)c, m);
                     ++nList;
                 }
@@ -519,6 +521,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
         }
         if (cacheQuads && !tileEmpty) {  // new tile: empty boxes contain nothing, so the first sample rebuilds
             for (int o = lane; o < nO - 1; o += 32) {
+                B2R_BOUND(o, nO - 1);
                 myCache[(size_t)o * cacheQuads] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f);
                 myCache[(size_t)o * cacheQuads + 1] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
             }
@@ -688,6 +691,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                         } else if (!cacheQuads) {
                                             if (any && !occluded) shadow_chunk(c * 32, wm);
                                         } else if (wm) {
+                                            B2R_BOUND(nSh, nChunks);
                                             if (lane == 0) shList[nSh] = make_uint2((unsigned)c, wm);
                                             ++nSh;
                                         }

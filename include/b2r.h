@@ -133,7 +133,10 @@ int b2r_ras_cull(b2r_ctx* ctx, uint8_t* culledOut);
  * Converts the pixelColours of the last draw on this context to the 32-bit
  * XRGB surface the reference fills (interior pixels only; the 1-pixel border
  * stays 0).  Applies the depth-of-field blur when params.dofEnabled.
- * surface: width*height uint32 (0x00RRGGBB), host memory. */
+ * surface: width*height uint32 (0x00RRGGBB), host memory.
+ * "Last draw" means a host-buffer draw (b2r_rt_draw / b2r_ras_draw with pixelColours, b2r_rt_frame, b2r_ras_frame):
+ * only those leave a frame in the context's own buffers.  After a *_device_async, *_part or *_bgr8 draw, or a draw
+ * without pixelColours, the resolve calls return B2R_E_NO_SCENE instead of an older image. */
 int b2r_resolve_surface(b2r_ctx* ctx, uint32_t* surface);
 /* Same pixels as 24-bit bottom-up BGR rows padded to 4 bytes (the payload
  * SDL_SaveBMP writes, raytracer.cpp:175).  bgr: b2r_bmp_payload_bytes(). */
@@ -168,6 +171,11 @@ void* b2r_get_stream(b2r_ctx* ctx);
 int b2r_synchronize(b2r_ctx* ctx);  /* also reports B2R_E_CAPACITY of asynchronous rasteriser draws since the last call */
 int b2r_rt_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_pixelColours,
                              b2r_intersection* d_closestIntersections, float* d_focalDistances);
+/* Rasteriser draws size their intermediate buffers from counters of the frame itself.  Small scenes (triangles x band
+ * height <= 2M) use fixed worst-case slots: the call only enqueues, and a projected triangle beyond the row/coordinate
+ * limits is reported by the next b2r_synchronize (B2R_E_CAPACITY).  Larger scenes read the counters back ONCE per
+ * (scene, isCulled flags, frame params, band): the first draw of a new state blocks the host for one stream
+ * synchronisation and reports B2R_E_CAPACITY itself; later draws of the same state only enqueue. */
 int b2r_ras_draw_device_async(b2r_ctx* ctx, int y0, int y1, float* d_depthBuffer,
                               float* d_pixelColours, float* d_focalDistances, int32_t* d_winnerIndex);
 /* Draw() for rows [y0,y1) in one call: trace (or rasterise) + shade + CalculateDOF/PutPixelSDL into d_surface (full-frame
