@@ -158,15 +158,18 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
 
     const int i = blockIdx.x * kSmallThreads + threadIdx.x;
     unsigned long long nTests = 0, nRows = 0, nDrawn = 0;
-    if (i < a.T && !(a.culled && a.culled[i])) {  // :470
-        // the three vertices: 9 floats at the head of the 64-byte record (60-byte scenes are repacked at upload)
-        float t[12];
-        {
-            const float4* q = reinterpret_cast<const float4*>(a.raw + (size_t)i * 64);
-            const float4 q0 = q[0], q1 = q[1], q2 = q[2];
-            t[0] = q0.x; t[1] = q0.y; t[2] = q0.z; t[3] = q0.w; t[4] = q1.x; t[5] = q1.y; t[6] = q1.z; t[7] = q1.w;
-            t[8] = q2.x; t[9] = q2.y; t[10] = q2.z; t[11] = q2.w;
-        }
+    // the three vertices: 9 floats at the head of the 64-byte record (60-byte scenes are repacked at upload), fetched
+    // together with the isCulled flag, which therefore does not gate the fetch
+    float t[12];
+    unsigned char isCulled = 1;
+    if (i < a.T) {
+        isCulled = a.culled ? a.culled[i] : (unsigned char)0;
+        const float4* q = reinterpret_cast<const float4*>(a.raw + (size_t)i * 64);
+        const float4 q0 = q[0], q1 = q[1], q2 = q[2];
+        t[0] = q0.x; t[1] = q0.y; t[2] = q0.z; t[3] = q0.w; t[4] = q1.x; t[5] = q1.y; t[6] = q1.z; t[7] = q1.w;
+        t[8] = q2.x; t[9] = q2.y; t[10] = q2.z; t[11] = q2.w;
+    }
+    if (!isCulled) {  // :470
         RPixel v[3];
         int maxY = INT_MIN, minY = INT_MAX;
         bool bad = false;
