@@ -23,6 +23,16 @@ def row_band(rank, world, height):
     return y0, y0 + base + (1 if rank < extra else 0)
 
 
+def tile_rows_for_part(part, nparts, height, tile_rows=8):
+    """Pixel rows of `height` drawn by `part` of a frame split `nparts` ways: tile rows (8 pixel rows) part,
+    part + nparts, ... -- interleaved, so that every part carries the same mix of cheap and expensive rows
+    (b2r_rt_frame_part / b2r_rt_frame_gather_device_async).  Returns a list of (y0, y1) row ranges."""
+    if not (0 <= part < nparts) or height < 0:
+        raise ValueError("bad part/nparts/height")
+    ntiles = (height + tile_rows - 1) // tile_rows
+    return [(t * tile_rows, min((t + 1) * tile_rows, height)) for t in range(part, ntiles, nparts)]
+
+
 def frames_for_rank(rank, world, nframes):
     """Frame indices rendered by `rank` when an animation is partitioned round-robin."""
     return list(range(rank, nframes, world))
