@@ -10,8 +10,11 @@ A "step" is one Draw() (trace + shade + resolve to the 32-bit surface) of ONE fr
 split: rank r traces tile rows r, r+N, ... and stores its pixels into the root GPU's surface over NVLink
 (b2r_rt_frame_gather_device_async); the last thread block of every launch bumps an arrival word in the root's
 memory and the root's stream waits for it on the GPU.  No collective, strong scaling.
-metric = Mrays/s, a ray being one ClosestIntersection call (primary + shadow rays actually cast,
-counted by the kernel's own counters in an untimed pass).
+metric = Mrays/s, a ray being one ClosestIntersection call of the reference's Draw() for this frame (primary rays +
+one shadow ray per hit sub-sample and light sample; counted by the kernel's own counters in an untimed pass and equal to
+the oracle's count).  The kernel answers every one of them with the reference's bits; extra.shadow_rays_evaluated says
+how many shadow rays it had to trace to do so (a sub-sample whose hit does not replace the pixel's carried Intersection
+shades the same point as the sub-sample before: DirectLight's value is reused).
 
   value         device-resident: inputs already in HBM, CUDA events around each step on the
                 launching stream, L2 flushed between steps, max over ranks.
@@ -395,6 +398,8 @@ def run_gpu_arm(args, pkg):
         shm.close()
 
     extra = {"frames_per_s": args.steps / (total_ms * 1e-3), "rays_per_frame": rays,
+             "primary_rays": st["primary_rays"], "shadow_rays": st["shadow_rays"],
+             "shadow_rays_evaluated": st["shadow_rays_evaluated"],
              "algorithmic_gflop_per_frame": flops / 1e9, "e2e_frames_per_s": args.steps / e2e_s,
              "split_verified": split_verified, "e2e_frame_verified": e2e_verified}
 

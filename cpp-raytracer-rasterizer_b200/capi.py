@@ -85,7 +85,7 @@ class FrameParams(C.Structure):
 
 
 STAT_NAMES = ["primary_rays", "shadow_rays", "exact_tests", "ras_triangles", "ras_rows", "ras_depth_tests",
-              "reserved6", "reserved7"]
+              "shadow_rays_evaluated", "reserved7"]
 
 # Every symbol include/b2r.h declares (tests check the library exports each one).
 SYMBOLS = [

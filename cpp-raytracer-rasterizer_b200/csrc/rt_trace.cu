@@ -187,7 +187,7 @@ struct PixelState {  // == struct Intersection (+ the focalDistances slot), rayt
 };
 
 struct Counters {
-    unsigned long long primary = 0, shadow = 0, exact = 0;
+    unsigned long long primary = 0, shadow = 0, exact = 0, shadowEval = 0;
 };
 
 constexpr int kTileW = 32, kTileH = 8, kThreads = 256;
@@ -534,6 +534,11 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
         ps.idx = -1;
         ps.focal = 0.f;
         V3 avg = mk3(0.f, 0.f, 0.f);
+        // DirectLight is a pure function of the pixel's carried Intersection (and the frame): a sub-sample whose hit did
+        // not replace it (:243) shades the same point of the same triangle as the sub-sample before, to the same bits.
+        // lastTerm keeps color * (DirectLight + indirectLight) of the last evaluation; the shading block (with its
+        // shadow rays) runs only for lanes whose Intersection changed, and not at all when no lane's did.
+        V3 lastTerm = mk3(0.f, 0.f, 0.f);
         float y1 = (N > 1) ? xsub((float)y, 0.5f) : (float)y;  // :564-567
         for (int z = 0; z < (tileEmpty ? 0 : N); ++z) {
             float x1 = (N > 1) ? xsub((float)x, 0.5f) : (float)x;  // :571-574
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                 // ---- primary ray :579-580
                 const float dx = xsub(x1, halfW), dy = xsub(y1, halfH);
                 V3 nd = mk3(0.f, 0.f, 0.f);
-                bool haveDir = false, any = false;
+                bool haveDir = false, any = false, changed = false;
                 if (inside) {
                     if constexpr (STATS) cnt.primary++;
                     for (int e = 0; e < nList; ++e) {
@@ -566,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                     ps.dist = dist;
                                     ps.idx = i;
                                     ps.focal = xsub(dist, dofFocal);  // :249
+                                    changed = true;
                                 }
                                 any = true;  // :251
                             }
@@ -574,9 +580,12 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                 }
                 // ---- DirectLight :265-327.  The warp stays converged so the shadow rays of all its
                 // hit pixels can be culled together; lanes without a hit only take part in the collectives.
-                if (__any_sync(kFull, any)) {
+                const bool lit = any && changed;  // this lane's Intersection was replaced: DirectLight has a new argument
+                if constexpr (STATS)
+                    if (any && !changed) cnt.shadow += (unsigned long long)(nO - 1);  // the reference casts them; same answer as before
+                if (__any_sync(kFull, lit)) {
                     V3 nDir = mk3(0.f, 0.f, 0.f), colr = mk3(0.f, 0.f, 0.f);
-                    if (any) {
+                    if (lit) {
                         const float4 g3 = sG[ps.idx * kGeomQuads + 3], g4 = sG[ps.idx * kGeomQuads + 4];
                         nDir = mk3(g3.x, g3.y, g3.z);
                         colr = mk3(g3.w, g4.x, g4.y);
@@ -606,11 +615,11 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                             const float r = xsqrt(rr);               // :294
                             const V3 rDir = xscale3(dv, xdiv(1.0f, r));  // :298 normalize
                             V3 D = mk3(0.f, 0.f, 0.f);
-                            if (any) {
+                            if (lit) {
                                 const float A = sphere_area(r);      // :295
                                 const V3 B = xdivs3_shared(P, A);    // :301
                                 D = xscale3(B, std_max(xdot3(rDir, nDir), 0.0f));  // :304
-                                if constexpr (STATS) cnt.shadow++;
+                                if constexpr (STATS) cnt.shadow++, cnt.shadowEval++;
                             }
                             // ---- shadow ray from the light towards the surface :307-315
                             // direction -rDir, so -dir == rDir; occluded iff any accepted hit is
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                 for (int c = 0; c < nChunks; ++c) {
                                     const int base = c * 32;
                                     const unsigned wm = (T - base >= 32) ? kFull : ((1u << (T - base)) - 1u);
-                                    if (any && !occluded) shadow_chunk(base, wm);
+                                    if (lit && !occluded) shadow_chunk(base, wm);
                                 }
                             } else {
                                 // Cached shadow candidates.  The warp mask of shadow_warp_mask() is valid for ANY
@@ -651,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                 bool cached = false;
                                 if (cacheQuads) {
                                     const float4 c0 = hdr[0], c1 = hdr[1];
-                                    const bool in = !any || (dv.x >= c0.x && dv.x <= c1.x && dv.y >= c0.y && dv.y <= c1.y &&
+                                    const bool in = !lit || (dv.x >= c0.x && dv.x <= c1.x && dv.y >= c0.y && dv.y <= c1.y &&
                                                              dv.z >= c0.z && dv.z <= c1.z);
                                     cached = __all_sync(kFull, in);
                                     if (cached) {
@@ -667,8 +676,8 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                     // the rounded values the lanes use.
                                     if (!haveBox) {
                                         const float big = 3.0e38f;
-                                        posLo = mk3(warp_min(any ? ps.pos.x : big), warp_min(any ? ps.pos.y : big), warp_min(any ? ps.pos.z : big));
-                                        posHi = mk3(warp_max(any ? ps.pos.x : -big), warp_max(any ? ps.pos.y : -big), warp_max(any ? ps.pos.z : -big));
+                                        posLo = mk3(warp_min(lit ? ps.pos.x : big), warp_min(lit ? ps.pos.y : big), warp_min(lit ? ps.pos.z : big));
+                                        posHi = mk3(warp_max(lit ? ps.pos.x : -big), warp_max(lit ? ps.pos.y : -big), warp_max(lit ? ps.pos.z : -big));
                                         haveBox = true;
                                     }
                                     V3 qlo = xsub3(lpos, posHi), qhi = xsub3(lpos, posLo);
@@ -689,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                         if (nChunks == 1) {
                                             wm0 = wm;
                                         } else if (!cacheQuads) {
-                                            if (any && !occluded) shadow_chunk(c * 32, wm);
+                                            if (lit && !occluded) shadow_chunk(c * 32, wm);
                                         } else if (wm) {
                                             B2R_BOUND(nSh, nChunks);
                                             if (lane == 0) shList[nSh] = make_uint2((unsigned)c, wm);
@@ -704,7 +713,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                                         __syncwarp();
                                     }
                                 }
-                                if (any) {
+                                if (lit) {
                                     if (nChunks == 1) {
                                         shadow_chunk(0, wm0);
                                     } else if (cacheQuads) {
@@ -727,12 +736,15 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                             }
                         }
                     }
-                    if (any) {
+                    if (lit) {
                         const V3 color = xmul3(result2, colr);  // :325-326
                         const V3 Tsum = xadd3(color, indirect); // :586
-                        avg = xadd3(avg, xmul3(colr, Tsum));    // :587-591
-                        x1 = xadd(x1, stepAA);                  // :593 -- only after a hit
+                        lastTerm = xmul3(colr, Tsum);           // :587-591
                     }
+                }
+                if (any) {
+                    avg = xadd3(avg, lastTerm);  // :587-591
+                    x1 = xadd(x1, stepAA);       // :593 -- only after a hit
                 }
             }
             y1 = xadd(y1, stepAA);  // :596
@@ -790,12 +802,13 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
     }
 
     if constexpr (STATS) {
-        unsigned long long v[3] = {cnt.primary, cnt.shadow, cnt.exact};
+        const unsigned long long v[4] = {cnt.primary, cnt.shadow, cnt.exact, cnt.shadowEval};
+        const int slot[4] = {B2R_STAT_PRIMARY_RAYS, B2R_STAT_SHADOW_RAYS, B2R_STAT_EXACT_TESTS, B2R_STAT_SHADOW_RAYS_EVALUATED};
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 4; ++k) {
             unsigned long long s = v[k];
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-            if (lane == 0 && s) atomicAdd(a.stats + k, s);
+            if (lane == 0 && s) atomicAdd(a.stats + slot[k], s);
         }
     }
 }

@@ -224,11 +224,15 @@ unsigned long long b2r_launch_count(const b2r_ctx* ctx);
 /* Counters of the last draw: see B2R_STAT_* indices; out must hold B2R_STAT_COUNT values. */
 enum {
     B2R_STAT_PRIMARY_RAYS = 0,  /* ClosestIntersection calls from Draw (raytracer.cpp:580) */
-    B2R_STAT_SHADOW_RAYS = 1,   /* ClosestIntersection calls from DirectLight (raytracer.cpp:310) */
+    B2R_STAT_SHADOW_RAYS = 1,   /* ClosestIntersection calls the reference makes from DirectLight (raytracer.cpp:310) for this draw */
     B2R_STAT_EXACT_TESTS = 2,   /* ray/triangle pairs that reached the exact (reference-order) evaluation */
     B2R_STAT_RAS_TRIANGLES = 3, /* triangles drawn (not culled) */
     B2R_STAT_RAS_ROWS = 4,      /* polygon rows produced by ComputePolygonRows */
     B2R_STAT_RAS_DEPTH_TESTS = 5, /* on-screen depth tests (rasteriser.cpp:606) */
+    B2R_STAT_SHADOW_RAYS_EVALUATED = 6, /* of SHADOW_RAYS, those whose DirectLight term was computed; the others belong to
+                                           sub-samples whose hit did not replace the pixel's carried Intersection
+                                           (raytracer.cpp:243): DirectLight has the same argument as for the sub-sample
+                                           before and its value is reused, bit for bit */
     B2R_STAT_COUNT = 8
 };
 int b2r_get_stats(b2r_ctx* ctx, unsigned long long* out);
