@@ -454,6 +454,7 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.bandDone = bandTileRows > 0 ? c->rtSched.as<unsigned>() + 16 : nullptr;
     a.bandTileRows = bandTileRows > 0 ? bandTileRows : 1;
     a.useFilter = c->optRtFilter;
+    a.reuseLight = c->optRtVariant == 5 ? 0 : 1;
     cudaError_t e = launch_rt_trace_shade(c, a, c->stream);
     if (e == cudaErrorInvalidConfiguration)
         return fail(c, B2R_E_UNSUPPORTED, "raytracer: more than ~100,000 triangles per scene are not supported by the brute-force tracer");

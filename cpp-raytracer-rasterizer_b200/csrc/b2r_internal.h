@@ -102,6 +102,7 @@ struct RtLaunch {
     unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
     int batch;         // warp tiles per scheduler fetch (set by the launcher)
     int useFilter;
+    int reuseLight;    // 1 (default): DirectLight only when the pixel's carried Intersection changed (see rt_trace.cu)
     int shadowCache;   // set by launch_rt_trace_shade: per-warp shadow-candidate cache in shared memory
 };
 

@@ -580,9 +580,9 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
                 }
                 // ---- DirectLight :265-327.  The warp stays converged so the shadow rays of all its
                 // hit pixels can be culled together; lanes without a hit only take part in the collectives.
-                const bool lit = any && changed;  // this lane's Intersection was replaced: DirectLight has a new argument
+                const bool lit = any && (changed || !a.reuseLight);  // this lane's Intersection was replaced: DirectLight has a new argument
                 if constexpr (STATS)
-                    if (any && !changed) cnt.shadow += (unsigned long long)(nO - 1);  // the reference casts them; same answer as before
+                    if (any && !lit) cnt.shadow += (unsigned long long)(nO - 1);  // the reference casts them; same answer as before
                 if (__any_sync(kFull, lit)) {
                     V3 nDir = mk3(0.f, 0.f, 0.f), colr = mk3(0.f, 0.f, 0.f);
                     if (lit) {
@@ -884,7 +884,7 @@ static cudaError_t launch_variant(Ctx* c, const RtLaunch& a, size_t smem, cudaSt
 
 // B2R_OPT_RT_VARIANT: 0 = tile/warp culling + per-ray filter (default); 1 = per-ray filter only;
 // 2 = like 0 but constants read from HBM even when they would fit in shared memory (tests the large-scene path);
-// 3 = like 0 without the shadow-candidate cache.
+// 3 = like 0 without the shadow-candidate cache; 5 = like 0, DirectLight evaluated for every hit sub-sample (no reuse).
 cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     const DevFrame& f = c->hostFrame;
     RtLaunch a = a0;
@@ -896,7 +896,7 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     if (resident) {
         a.xconst = a.fconst = nullptr;
         if (a.T <= 32) {
-            if (f.nLights == 1 && f.samples == 1 && f.nOrigins == 2 && c->optRtVariant == 0) {
+            if (f.nLights == 1 && f.samples == 1 && f.nOrigins == 2 && (c->optRtVariant == 0 || c->optRtVariant == 5)) {
                 for (int i = 0; i < 3; ++i) a.fr.light0[i] = f.origin[1][i], a.fr.power0[i] = f.lightPower[0][i];
                 return launch_variant<true, true, true, true>(c, a, smemRes, s);
             }

@@ -241,7 +241,7 @@ int b2r_enable_stats(b2r_ctx* ctx, int on);
 /* Tuning/diagnostic switches (B2R_OPT_*); results are identical for every setting. */
 enum {
     B2R_OPT_RT_FILTER = 0,   /* 1 (default): conservative FMA filter ahead of the exact reference-order test; 0: exact test on every ray/triangle pair */
-    B2R_OPT_RT_VARIANT = 1,  /* 0 all culling levels (default); 1 per-ray filter only; 2 force the large-scene path; 3 no shadow-candidate cache; 4 host-buffer draws use one launch per sub-band instead of stream wait-value operations */
+    B2R_OPT_RT_VARIANT = 1,  /* 0 all culling levels (default); 1 per-ray filter only; 2 force the large-scene path; 3 no shadow-candidate cache; 4 host-buffer draws use one launch per sub-band instead of stream wait-value operations; 5 DirectLight evaluated for every hit sub-sample instead of once per carried Intersection */
     B2R_OPT_RAS_VARIANT = 2, /* 0 sort-last pipeline (default); 1 the same, never using the fixed-slot (no readback) large-triangle path of small scenes; 2 screen-tile pipeline (binning + per-tile raster/shade in shared memory); 3 the same without fixed slots */
     B2R_OPT_DOF_VARIANT = 3  /* 0 shared-memory tiled kernel when dofKernelSize == 8 (default); 1 always the generic kernel */
 };

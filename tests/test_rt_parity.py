@@ -232,3 +232,40 @@ def test_stl_sized_scene(pkg, oracle):
     ctx.set_frame(fp)
     check(ctx.rt_draw(), oracle.rt_draw(tris, fp, w, h))
     ctx.close()
+
+
+@pytest.mark.parametrize("aa,soft,nlights", [(0, 0, 1), (4, 0, 1), (3, 1, 1), (2, 0, 3)])
+def test_direct_light_reuse_is_exact(pkg, oracle, aa, soft, nlights):
+    """DirectLight is evaluated once per carried Intersection (a sub-sample whose hit does not replace the pixel's
+    Intersection, raytracer.cpp:243, shades the same point as the one before).  Variant 5 evaluates it for every hit
+    sub-sample like the reference: every array must be bit-identical either way, the ray counters must be the reference's
+    in both, and only the 'evaluated' counter may differ."""
+    rng = np.random.default_rng(100 + aa + 10 * soft + nlights)
+    w, h = 200, 120
+    tris = np.concatenate([pkg.cornell_box(), random_soup(rng, 12, spread=0.8, size=0.5)])
+    fp = pkg.default_frame_params(0, w, h)
+    fp.aaEnabled, fp.aaSamples, fp.softShadowsEnabled, fp.softShadowsSamples = int(aa > 0), max(aa, 1), soft, 4
+    fp.set_camera([0.15, -0.1, -2.2], rot_y(0.2), h / 2)
+    lights = np.array([[0, -0.5, -0.7, 1, 1, 1, 14], [0.6, -0.6, -0.2, 0.9, 0.7, 0.4, 6], [-0.5, 0.2, -0.9, 0.3, 0.5, 1.0, 9]], np.float32)[:nlights]
+    fp.set_lights(lights)
+    fp.set_random_positions(rng.uniform(-1, 1, (256, 3)).astype(np.float32))
+    want = oracle.rt_draw(tris, fp, w, h)
+    out = {}
+    for variant in (0, 5):
+        ctx = pkg.Context(w, h)
+        ctx.set_option(pkg.capi.OPT_RT_VARIANT, variant)
+        ctx.enable_stats(True)
+        ctx.set_triangles(tris)
+        ctx.set_frame(fp)
+        got = ctx.rt_draw()
+        st = ctx.stats()
+        ctx.close()
+        check(got, want)
+        assert st["primary_rays"] == want["primary_rays"] and st["shadow_rays"] == want["shadow_rays"]
+        out[variant] = st
+    assert out[5]["shadow_rays_evaluated"] == out[5]["shadow_rays"]
+    assert out[0]["shadow_rays_evaluated"] <= out[0]["shadow_rays"]
+    if aa == 0:
+        assert out[0]["shadow_rays_evaluated"] == out[0]["shadow_rays"]  # one sub-sample per pixel: nothing to reuse
+    else:
+        assert out[0]["shadow_rays_evaluated"] < out[0]["shadow_rays"]

@@ -72,7 +72,7 @@ def test_soak_random_frames(pkg, oracle):
         # ---- raytracer
         tris, fp, w, h = _random_rt_case(pkg, rng)
         ctx = pkg.Context(w, h)
-        ctx.set_option(pkg.capi.OPT_RT_VARIANT, int(rng.choice([0, 0, 0, 1, 2, 3])))
+        ctx.set_option(pkg.capi.OPT_RT_VARIANT, int(rng.choice([0, 0, 0, 1, 2, 3, 5])))
         ctx.set_triangles(tris)
         ctx.set_frame(fp)
         want = oracle.rt_draw(tris, fp, w, h)
