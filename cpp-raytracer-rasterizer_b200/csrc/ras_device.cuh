@@ -1,4 +1,4 @@
-// ras_device.cuh -- device functions of the rasteriser shared by the frame pipeline (ras_pipeline.cu) and the
+// ras_device.cuh -- device functions of the rasteriser shared by the frame pipelines (ras_sortlast.cu, ras_tiles.cu) and the
 // sub-stage entry points (substage_kernels.cu).  Reference-order arithmetic only (see exact.cuh).
 #pragma once
 #include <limits.h>
