@@ -518,6 +518,30 @@ def run_gpu_arm(args, pkg):
         barrier()
         ctx.shared_free(mine)
 
+    # the same frame through the single-process group ABI (b2r_group_rt_frame: what host/raytracer_dropin.cpp's Draw()
+    # calls with several devices): rank 0 drives every GPU of the job while the other ranks wait
+    barrier()
+    if rank == 0 and world > 1 and torch.cuda.device_count() >= world:
+        try:
+            grp = pkg.Group(W4K, H4K, list(range(world)))
+            grp.set_triangles(tris)
+            gsurf = torch.empty((H4K, W4K), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+            for _ in range(3):
+                grp.set_frame(fp)
+                grp.rt_frame(gsurf)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                grp.set_frame(fp)
+                grp.rt_frame(gsurf)
+            gs = (time.perf_counter() - t0) / args.steps
+            ctx.rt_frame_device_async(0, H4K, d_surf.data_ptr())
+            ctx.synchronize()
+            extra["group_rt_frame_e2e"] = {"ms_per_frame": gs * 1e3, "value": rays / gs / 1e6, "unit": "Mrays/s",
+                                           "verified": bool(np.array_equal(gsurf, d_surf.cpu().numpy().view(np.uint32))),
+                                           "call": f"b2r_group_set_frame + b2r_group_rt_frame, one process driving {world} GPUs"}
+            grp.close()
+        except Exception as ex:
+            extra["group_rt_frame_e2e"] = {"error": repr(ex)}
     barrier()
     if world > 1 and rank != 0:
         ctx.shared_close(root)
