@@ -521,6 +521,10 @@ def run_gpu_arm(args, pkg):
     # the same frame through the single-process group ABI (b2r_group_rt_frame: what host/raytracer_dropin.cpp's Draw()
     # calls with several devices): rank 0 drives every GPU of the job while the other ranks wait
     barrier()
+    done_flag = f"/dev/shm/b2r_group_done_{os.environ.get('MASTER_PORT', '0')}"
+    if rank == 0 and os.path.exists(done_flag):
+        os.unlink(done_flag)
+    barrier()
     if rank == 0 and world > 1 and torch.cuda.device_count() >= world:
         try:
             grp = pkg.Group(W4K, H4K, list(range(world)))
@@ -542,7 +546,17 @@ def run_gpu_arm(args, pkg):
             grp.close()
         except Exception as ex:
             extra["group_rt_frame_e2e"] = {"error": repr(ex)}
+    # the other ranks wait on the host (a flag file), not in an NCCL barrier whose kernel would share their GPU with
+    # rank 0's group members
+    if rank == 0:
+        open(done_flag, "w").close()
+    else:
+        torch.cuda.synchronize(dev)
+        while not os.path.exists(done_flag):
+            time.sleep(0.005)
     barrier()
+    if rank == 0 and os.path.exists(done_flag):
+        os.unlink(done_flag)
     if world > 1 and rank != 0:
         ctx.shared_close(root)
     barrier()

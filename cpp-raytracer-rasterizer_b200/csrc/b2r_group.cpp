@@ -27,8 +27,9 @@ struct b2r_group {
     std::vector<int> dev;
     std::vector<b2r_ctx*> ctx;
     std::string err;
-    void* pinned = nullptr;  // caller surface page-locked on the caller's behalf (last one seen)
-    size_t pinnedBytes = 0;
+    void* pinned = nullptr;  // caller surface page-locked on the caller's behalf
+    void* seen = nullptr;    // last caller surface looked at (locked by us or already by the caller)
+    size_t seenBytes = 0;
 };
 
 namespace {
@@ -52,16 +53,18 @@ int member_fail(b2r_group* g, int i, int rc, const char* what) {
 // it), remembered until the caller passes a different buffer.  Failure to lock is not an error: the copies then go
 // through the driver's staging buffer.
 void pin_for_group(b2r_group* g, void* p, size_t bytes) {
-    if (g->pinned == p && g->pinnedBytes >= bytes) return;
+    if (g->seen == p && g->seenBytes >= bytes) return;  // this buffer has been dealt with (locked here, or by the caller)
     if (g->pinned) cudaHostUnregister(g->pinned);
     g->pinned = nullptr;
-    g->pinnedBytes = 0;
-    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
-    if (e == cudaSuccess) {
-        g->pinned = p;
-        g->pinnedBytes = bytes;
+    g->seen = p;
+    g->seenBytes = bytes;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return;  // already page-locked by the caller (cudaHostAlloc / cudaHostRegister)
     }
-    cudaGetLastError();  // already registered by the caller, or not lockable: both fine
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess) g->pinned = p;
+    cudaGetLastError();  // not lockable: fine, the copies go through the driver's staging buffer
 }
 
 // ---- writer threads of b2r_group_rt_frames: BMP files (or copies into the caller's array) off the GPU threads ----
