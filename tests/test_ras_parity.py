@@ -175,3 +175,17 @@ def test_vertex_behind_camera_is_refused(pkg, ras_variant):
     ctx.ras_draw_device_async(0, h, 0, col.data_ptr())
     ctx.synchronize()
     ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 2], ids=["sortlast", "tiles"])
+def test_more_than_2_pow_20_triangles(pkg, oracle, variant):
+    """1,083,000 sub-pixel triangles on a small screen: the tile pipeline's depth key holds 20 bits of the triangle index,
+    so this scene is drawn in two epochs (indices below / from 2^20) with the keys frozen in between; tile lists run to
+    tens of thousands of entries, i.e. many jobs per tile merged through the partial-result slots."""
+    w, h = 320, 180
+    tris = np.ascontiguousarray(pkg.tessellate(pkg.cornell_box(), 190)[::-1])  # reversed: the floor gets the highest indices
+    assert len(tris) == 30 * 190 * 190 > (1 << 20)
+    fp = pkg.default_frame_params(1, w, h)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, variant=variant)
+    check(got, want)
+    assert (got["winner"] >= (1 << 20)).any() and (got["winner"] < (1 << 20)).any()
