@@ -189,3 +189,29 @@ def test_more_than_2_pow_20_triangles(pkg, oracle, variant):
     got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, variant=variant)
     check(got, want)
     assert (got["winner"] >= (1 << 20)).any() and (got["winner"] < (1 << 20)).any()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_wide_flat_triangles(pkg, oracle, variant):
+    """Triangles of a few rows that span thousands of columns: in the tile pipeline they are wider than the 128-tile
+    rectangle a small triangle may have and take the large-triangle path; long spans cross many tiles."""
+    w, h = 6000, 48
+    rng = np.random.default_rng(3)
+    n = 24
+    tris = np.zeros((n, 15), np.float32)
+    for i in range(n):
+        y = rng.uniform(-0.018, 0.018)
+        z = rng.uniform(0.5, 3.0)
+        v0 = [rng.uniform(-1.2, -0.6), y, z]
+        v1 = [rng.uniform(0.6, 1.2), y + rng.uniform(-0.004, 0.004), z + rng.uniform(-0.3, 0.3)]
+        v2 = [rng.uniform(-0.3, 0.3), y + rng.uniform(0.002, 0.01), z + rng.uniform(-0.3, 0.3)]
+        tris[i, 0:9] = v0 + v1 + v2
+        e1, e2 = tris[i, 3:6] - tris[i, 0:3], tris[i, 6:9] - tris[i, 0:3]
+        nrm = np.cross(e2, e1)
+        tris[i, 9:12] = nrm / np.linalg.norm(nrm)
+        tris[i, 12:15] = rng.uniform(0.2, 0.9, 3)
+    fp = pkg.default_frame_params(1, w, h)
+    fp.set_camera([0.0, 0.0, -2.0], rot_y(0.0, 1.01), 2400.0)
+    got, want, _ = draw_both(pkg, oracle, tris, fp, w, h, cull=False, variant=variant)
+    check(got, want)
+    assert (want["winner"] >= 0).sum() > 20000

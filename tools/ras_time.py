@@ -6,14 +6,18 @@ import __graft_entry__ as g
 pkg = g.load_package()
 
 
+VARIANTS = tuple(int(v) for v in os.environ.get('RAS_VARIANTS', '0,4').split(','))
+SIZES = os.environ.get('RAS_SIZES', '183').split(',')
+
+
 def main():
     dev = torch.device("cuda:0")
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tris = pkg.cornell_box()
-    for (w, h, k) in [(500, 500, 1), (3840, 2160, 1), (3840, 2160, 16), (3840, 2160, 183)]:
+    for (w, h, k) in [(3840, 2160, int(k)) for k in SIZES]:
         t = pkg.tessellate(tris, k) if k > 1 else tris
-        for variant in (0, 2):
+        for variant in VARIANTS:
             ctx = pkg.Context(w, h)
             ctx.set_option(pkg.capi.OPT_RAS_VARIANT, variant)
             ctx.set_stream(stream.cuda_stream)
