@@ -516,9 +516,14 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
                                                        const unsigned* __restrict__ rowOwner, unsigned nRows,
                                                        RowRec* __restrict__ rows,
                                                        unsigned long long* __restrict__ keys, int W, int y0,
-                                                       int y1, unsigned long long* __restrict__ stats) {
-    const unsigned rid = blockIdx.x * blockDim.x + threadIdx.x;
+                                                       int y1, unsigned long long* __restrict__ stats, int rowsPerWarp) {
+    // A warp takes rowsPerWarp (a power of two, 1..32) consecutive polygon rows, one per low lane; the other lanes
+    // only help with the long rows.  Few rows per warp when there are few rows in all (30 large triangles): the long
+    // rows of a warp are walked one after the other, so the number of warps is what spreads them over the SMs.
     const int lane = threadIdx.x & 31;
+    const unsigned warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool rowLane = lane < rowsPerWarp;
+    const unsigned rid = warpId * (unsigned)rowsPerWarp + (unsigned)lane;
     int lx = 0, pixels = 0, i0 = 0, i1 = 0, y = 0;
     float lz = 0.f, zstep = 0.f;
     unsigned tri = 0;
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
     // BAND: thread rid <-> (slot rid / bandH, row y0 + rid % bandH); otherwise the rows of the listed triangles are
     // packed and rowOwner names the triangle
     const unsigned slot = BAND ? rid / (unsigned)bandH : 0u;
-    if (BAND ? slot < ctr->nBig : rid < nRows) {
+    if (rowLane && (BAND ? slot < ctr->nBig : rid < nRows)) {
         const TriSetup s = ts[BAND ? slot : rowOwner[rid]];
         tri = (unsigned)s.tri;
         y = BAND ? y0 + (int)(rid - slot * (unsigned)bandH) : s.minY + (int)(rid - s.rowBase);
@@ -677,6 +682,14 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // sequence of launches.  Larger scenes size the buffers from counters read back after the first kernel.
 constexpr size_t kBandSlotLimit = 2u << 20;
 
+// rows per warp of ras_rows: enough warps to fill the machine (about 48 per SM) before a warp takes more than one row
+static inline int rows_per_warp(size_t nRows, int smCount) {
+    const size_t want = nRows / ((size_t)smCount * 48);
+    int r = 1;
+    while (r < 32 && (size_t)(2 * r) <= want) r *= 2;
+    return r;
+}
+
 }  // namespace sl
 
 using namespace sl;
@@ -747,8 +760,9 @@ cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s
         EdgeSample* samples = reinterpret_cast<EdgeSample*>(rb + align_up(sizeof(RowRec) * nSlots, 256));
         rowsPtr = rows;
         ras_edges_kernel<true><<<(15 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, nullptr, a.y0, a.y1);
-        ras_rows_kernel<true><<<(unsigned)((nSlots + 255) / 256), 256, 0, s>>>(ts, ctr, samples, nullptr, 0u, rows, keys, a.W, a.y0,
-                                                                              a.y1, a.stats);
+        const int rpw = rows_per_warp(nSlots, c->smCount);
+        ras_rows_kernel<true><<<(unsigned)((nSlots / rpw + 1 + 7) / 8), 256, 0, s>>>(ts, ctr, samples, nullptr, 0u, rows, keys, a.W, a.y0,
+                                                                                    a.y1, a.stats, rpw);
         c->launches += 2;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         c->rasErrPending = true;  // checked by the caller's next synchronising call (ras_take_error)
@@ -798,7 +812,8 @@ cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
         scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
         ras_edges_kernel<false><<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, ctr, samples, owner, a.y0, a.y1);
-        ras_rows_kernel<false><<<(nRows + 255) / 256, 256, 0, s>>>(ts, ctr, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats);
+        const int rpw = rows_per_warp(nRows, c->smCount);
+        ras_rows_kernel<false><<<(nRows / rpw + 1 + 7) / 8, 256, 0, s>>>(ts, ctr, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats, rpw);
         c->launches += 5;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -41,15 +41,18 @@ def test_resolve_surface_and_bmp(pkg, oracle, which, dof, tmp_path):
     ctx.close()
 
 
-def test_bmp_row_padding(pkg, oracle):
-    w, h = 33, 17  # 99 bytes per row -> padded to 100
+@pytest.mark.parametrize("w", [33, 34, 35, 36, 37, 38, 39, 40, 1, 2, 3, 4, 5])
+def test_bmp_row_padding(pkg, oracle, w):
+    """Every residue of W modulo 4 (the conversion kernel packs 4 pixels into 3 words) and of the row length modulo 4
+    (33 pixels: 99 bytes per row -> padded to 100)."""
+    h = 17
     fp = pkg.default_frame_params(0, w, h)
     ctx = pkg.Context(w, h)
     ctx.set_triangles(pkg.cornell_box())
     ctx.set_frame(fp)
     out = ctx.rt_draw()
     bgr = ctx.resolve_bgr8()
-    assert len(bgr) == 100 * h
+    assert len(bgr) == ((3 * w + 3) // 4 * 4) * h
     assert np.array_equal(bgr, oracle.surface_to_bgr8(oracle.resolve_surface(out["pixelColours"], None)))
     ctx.close()
 

@@ -3,5 +3,5 @@
 L=$PWD/cpp-raytracer-rasterizer_b200/lib
 for v in "$@"; do
   if [ "$v" = base ]; then lib=$L/libb2r.so; else lib=$L/libb2r_$v.so; fi
-  echo "== $v: $(B2R_LIB=$lib RAS_VARIANTS=${RAS_VARIANTS:-0} python tools/ras_time.py 2>&1 | tail -1)"
+  B2R_LIB=$lib RAS_VARIANTS=${RAS_VARIANTS:-0} python tools/ras_time.py 2>&1 | grep "^ras variant" | sed "s/^/== $v: /"
 done

@@ -7,7 +7,7 @@ pkg = g.load_package()
 
 
 VARIANTS = tuple(int(v) for v in os.environ.get('RAS_VARIANTS', '0,4').split(','))
-SIZES = os.environ.get('RAS_SIZES', '183').split(',')
+CASES = [tuple(int(v) for v in c.split('x')) for c in os.environ.get('RAS_CASES', '3840x2160x183').split(',')]  # WxHxtessellation
 
 
 def main():
@@ -15,7 +15,7 @@ def main():
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     tris = pkg.cornell_box()
-    for (w, h, k) in [(3840, 2160, int(k)) for k in SIZES]:
+    for (w, h, k) in CASES:
         t = pkg.tessellate(tris, k) if k > 1 else tris
         for variant in VARIANTS:
             ctx = pkg.Context(w, h)
