@@ -66,11 +66,11 @@ struct EdgeSample {  // 5 words
     float p[3];
 };
 
-struct RowRec {  // 12 words: left/right ends of one polygon row (y implied)
+struct RowRec {  // 12 words: left/right ends of one polygon row (y implied) and Bresenham's step of pos3d.xy (:649)
     int lx, rx;
     float lz, rz;
     float lp[3], rp[3];
-    int pad[2];
+    float psx, psy;  // only rows with fragments have them (pixels > 0)
 };
 
 constexpr int kMaxRowsPerTriangle = 1 << 22;
@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
                 s.rowBase = slot * bandH;
                 s.sampleBase = slot * 3u * bandH;
                 bigTs[slot] = s;
-                triInfo[i] = make_int2((int)slot, a.y0);
+                triInfo[i] = make_int2((int)s.rowBase, a.y0);  // row record of y: rowBase + (y - y0)
             } else {
                 bigTs[slot] = s;
                 bigCounts[slot] = make_uint2((unsigned)rows, samples);
-                triInfo[i] = make_int2((int)slot, minY);
+                triInfo[i] = make_int2(0, minY);  // .x = rowBase once scan_apply knows it: row record of y at rowBase + (y - minY)
             }
             nDrawn = 1;
             nRows = (unsigned long long)rows;
@@ -373,12 +373,13 @@ __global__ void scan_sums_kernel(uint2* __restrict__ blockSums, int nBlocks, uin
 }
 
 __global__ void scan_apply_kernel(const uint2* __restrict__ ex, const uint2* __restrict__ blockSums,
-                                  TriSetup* __restrict__ ts, int n) {
+                                  TriSetup* __restrict__ ts, int2* __restrict__ triInfo, int n) {
     int i = blockIdx.x * kScanBlock + threadIdx.x;
     if (i >= n) return;
     uint2 o = add2(ex[i], blockSums[blockIdx.x]);
     ts[i].rowBase = o.x;
     ts[i].sampleBase = o.y;
+    triInfo[ts[i].tri].x = (int)o.x;  // for the shade pass: one load from the winner's index to its row records
 }
 
 // ---- stage 2: Interpolate (:615-637), one thread per (triangle, edge) --------
@@ -471,7 +472,7 @@ __device__ __forceinline__ RowRec resolve_row(const TriSetup& s, const EdgeSampl
     r.rx = -INT_MAX;   // :697
     r.lz = r.rz = 0.f;
     r.lp[0] = r.lp[1] = r.lp[2] = r.rp[0] = r.rp[1] = r.rp[2] = 0.f;
-    r.pad[0] = r.pad[1] = 0;
+    r.psx = r.psy = 0.f;
     unsigned off = s.sampleBase;
     for (int e = 0; e < 3; ++e) {  // edge order 0->1, 1->2, 2->0 (:705-707)
         const int j = (e + 1) % 3;
@@ -538,14 +539,19 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
         // DrawRows (:743): rows with y outside the screen are skipped; outside the band: another GPU's
         if (y >= y0 && y < y1 && y >= s.minY && y < s.minY + s.rows) {
             RowRec r = BAND ? resolve_row(s, samples, y, bandH, y0) : resolve_row(s, samples, y);
-            rows[rid] = r;
             lx = r.lx;
             lz = r.lz;
             pixels = r.rx - r.lx;                              // :598
             i0 = max(0, -lx - 1);                              // :663 x >= 0
             i1 = min(pixels, W - lx - 1);                      //      x <  W
             if (i1 < i0) i1 = i0;
-            if (i1 > i0) zstep = xdiv_step(xsub(r.rz, r.lz), (float)pixels);  // :648
+            if (i1 > i0) {
+                const float fdx = (float)pixels;
+                zstep = xdiv_step(xsub(r.rz, r.lz), fdx);      // :648
+                r.psx = xdiv_step(xsub(r.rp[0], r.lp[0]), fdx);  // :649, once per row instead of once per shaded pixel
+                r.psy = xdiv_step(xsub(r.rp[1], r.lp[1]), fdx);
+            }
+            rows[rid] = r;
         }
     }
     const int count = i1 - i0;
@@ -585,14 +591,16 @@ __device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long
     ShadeIn in;
     const unsigned tri = key_triangle(key);
     if (key & 1ull) {
-        const int2 info = triInfo[tri];  // (slot in the large-triangle list, minY)
-        const RowRec r = rows[bigTs[info.x].rowBase + (unsigned)(y - info.y)];
-        const float fdx = (float)(r.rx - r.lx);  // :598, :649
-        in.lx = r.lx;
-        in.lpx = r.lp[0];
-        in.lpy = r.lp[1];
-        in.psx = xdiv_step(xsub(r.rp[0], r.lp[0]), fdx);
-        in.psy = xdiv_step(xsub(r.rp[1], r.lp[1]), fdx);
+        const int2 info = triInfo[tri];  // (index of the triangle's first row record, the y of that record)
+        const RowRec* r = rows + ((unsigned)info.x + (unsigned)(y - info.y));
+        const float4 q0 = *reinterpret_cast<const float4*>(r);          // lx, rx, lz, rz
+        const float2 q1 = *reinterpret_cast<const float2*>(r->lp);      // lp.x, lp.y
+        const float2 q2 = *reinterpret_cast<const float2*>(&r->psx);    // psx, psy
+        in.lx = __float_as_int(q0.x);
+        in.lpx = q1.x;
+        in.lpy = q1.y;
+        in.psx = q2.x;
+        in.psy = q2.y;
     } else {
         const float4* q = reinterpret_cast<const float4*>(rowRec + small_row_slot(tri, y));
         const float4 q0 = q[0], q1 = q[1];
@@ -682,6 +690,10 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // sequence of launches.  Larger scenes size the buffers from counters read back after the first kernel.
 constexpr size_t kBandSlotLimit = 2u << 20;
 
+// threads per CTA of ras_edges: one warp per CTA while that leaves SMs without one -- each thread issues one scattered
+// store per step of its chain, and the few warps of a 30-triangle scene would otherwise queue on four SMs' LSUs
+static inline int edges_block(int threads, int smCount) { return threads <= smCount * 32 * 4 ? 32 : 128; }
+
 // rows per warp of ras_rows: enough warps to fill the machine (about 48 per SM) before a warp takes more than one row
 static inline int rows_per_warp(size_t nRows, int smCount) {
     const size_t want = nRows / ((size_t)smCount * 48);
@@ -759,7 +771,8 @@ cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s
         RowRec* rows = reinterpret_cast<RowRec*>(rb);
         EdgeSample* samples = reinterpret_cast<EdgeSample*>(rb + align_up(sizeof(RowRec) * nSlots, 256));
         rowsPtr = rows;
-        ras_edges_kernel<true><<<(15 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, nullptr, a.y0, a.y1);
+        const int eb = edges_block(15 * T, c->smCount);
+        ras_edges_kernel<true><<<(15 * T + eb - 1) / eb, eb, 0, s>>>(ts, T, ctr, samples, nullptr, a.y0, a.y1);
         const int rpw = rows_per_warp(nSlots, c->smCount);
         ras_rows_kernel<true><<<(unsigned)((nSlots / rpw + 1 + 7) / 8), 256, 0, s>>>(ts, ctr, samples, nullptr, 0u, rows, keys, a.W, a.y0,
                                                                                     a.y1, a.stats, rpw);
@@ -810,8 +823,9 @@ cudaError_t launch_ras_draw_sortlast(Ctx* c, const RasLaunch& a0, cudaStream_t s
         rowsPtr = rows;
         scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, nBig);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
-        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, nBig);
-        ras_edges_kernel<false><<<(15 * nBig + 127) / 128, 128, 0, s>>>(ts, nBig, ctr, samples, owner, a.y0, a.y1);
+        scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, triInfo, nBig);
+        const int eb = edges_block(15 * nBig, c->smCount);
+        ras_edges_kernel<false><<<(15 * nBig + eb - 1) / eb, eb, 0, s>>>(ts, nBig, ctr, samples, owner, a.y0, a.y1);
         const int rpw = rows_per_warp(nRows, c->smCount);
         ras_rows_kernel<false><<<(nRows / rpw + 1 + 7) / 8, 256, 0, s>>>(ts, ctr, samples, owner, nRows, rows, keys, a.W, a.y0, a.y1, a.stats, rpw);
         c->launches += 5;

@@ -1115,7 +1115,8 @@ static cudaError_t launch_ras_draw_tiles(Ctx* c, const RasLaunch& a0, cudaStream
     }
     if (bandSlots) {
         if (T > 0) {
-            ras_edges_kernel<true><<<(12 * T + 127) / 128, 128, 0, s>>>(ts, T, ctr, samples, a.y0, a.y1);
+            const int eb = 12 * T <= c->smCount * 32 * 4 ? 32 : 128;  // one warp per CTA while SMs would be left without one
+            ras_edges_kernel<true><<<(12 * T + eb - 1) / eb, eb, 0, s>>>(ts, T, ctr, samples, a.y0, a.y1);
             c->launches++;
         }
     } else if (nBig > 0) {
@@ -1123,7 +1124,8 @@ static cudaError_t launch_ras_draw_tiles(Ctx* c, const RasLaunch& a0, cudaStream
         scan_blocks_kernel<<<nb, kScanBlock, 0, s>>>(counts, excl, sums, (int)nBig);
         scan_sums_kernel<<<1, kScanBlock, 0, s>>>(sums, nb, totals);
         scan_apply_kernel<<<nb, kScanBlock, 0, s>>>(excl, sums, ts, (int)nBig);
-        ras_edges_kernel<false><<<(12 * (int)nBig + 127) / 128, 128, 0, s>>>(ts, (int)nBig, ctr, samples, a.y0, a.y1);
+        const int eb = 12 * (int)nBig <= c->smCount * 32 * 4 ? 32 : 128;
+        ras_edges_kernel<false><<<(12 * (int)nBig + eb - 1) / eb, eb, 0, s>>>(ts, (int)nBig, ctr, samples, a.y0, a.y1);
         c->launches += 4;
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
