@@ -190,7 +190,11 @@ int b2r_group_rt_frames(b2r_group* g, const b2r_frame_params* frames, int nframe
     const bool bmp = bmp_pattern != nullptr;
     const size_t npx = (size_t)g->W * g->H;
     const size_t slotBytes = bmp ? b2r_bmp_payload_bytes(g->W, g->H) : npx * 4;
-    const int kRing = 3, nSlots = g->n * kRing;
+    // Per device: up to kInFlight frames on the GPU, the other slots of its ring with the writer threads.  Writing a 25 MB
+    // file takes several milliseconds (a frame is traced and copied in well under one), so what sets the pace is how
+    // many files are being written at once.
+    // many files are being written at once (one GPU, 4K, /dev/shm: 3 slots 130-195 frames/s, 8 slots 520, 12 slots 550).
+    const int kRing = 8, kInFlight = 2, nSlots = g->n * kRing;
     std::vector<void*> slots(nSlots, nullptr);
     int rcAll = B2R_OK;
     for (int s = 0; s < nSlots && !rcAll; ++s)
@@ -240,7 +244,7 @@ int b2r_group_rt_frames(b2r_group* g, const b2r_frame_params* frames, int nframe
     };
     if (!rcAll) {
         unsigned hw = std::thread::hardware_concurrency();
-        const int nThreads = (int)std::max(1u, std::min(hw ? hw : 4u, (unsigned)(4 * g->n)));
+        const int nThreads = (int)std::max(1u, std::min(hw ? hw : 4u, (unsigned)((kRing - kInFlight) * g->n)));
         for (int t = 0; t < nThreads; ++t) w.threads.emplace_back(work);
     }
     // per device: frames in flight as (frame, slot), oldest first
@@ -268,7 +272,7 @@ int b2r_group_rt_frames(b2r_group* g, const b2r_frame_params* frames, int nframe
             if (next[i] >= nframes) continue;
             more = true;
             const int slot = i * kRing + ringPos[i];
-            if ((int)flight[i].size() == kRing - 1) rcAll = retire(i);  // keep one slot with the writers at least
+            if ((int)flight[i].size() == kInFlight) rcAll = retire(i);
             if (rcAll) break;
             {   // the slot's previous frame must have been written out
                 std::unique_lock<std::mutex> lk(w.m);
