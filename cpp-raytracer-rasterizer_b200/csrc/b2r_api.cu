@@ -453,6 +453,10 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.arriveCtr = c->rtSched.as<unsigned>() + 2;
     a.bandDone = bandTileRows > 0 ? c->rtSched.as<unsigned>() + 16 : nullptr;
     a.bandTileRows = bandTileRows > 0 ? bandTileRows : 1;
+    // Bottom to top unless sub-bands are copied out in row order behind the tracing: the rows a launch ends with set
+    // the length of its tail (warps run out of tiles one warp tile apart), and the top rows of a frame -- ceiling, far
+    // walls -- are the cheap ones (a quarter of config 3 alone: 234 -> 223 us, a half: 408 -> 399 us).
+    a.tileOrder = a.bandDone ? 0 : 1;
     a.useFilter = c->optRtFilter;
     a.reuseLight = c->optRtVariant == 5 ? 0 : 1;
     cudaError_t e = launch_rt_trace_shade(c, a, c->stream);

@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
     int nextBase = base < numWarpTiles ? fetch_batch() : numWarpTiles;
     for (; base < numWarpTiles; base = nextBase, nextBase = nextBase < numWarpTiles ? fetch_batch() : numWarpTiles)
     for (int wt = base; wt < min(base + batch, numWarpTiles); ++wt) {
-        const int tile = wt >> 3, sub = wt & 7;
+        const int tile = a.tileOrder ? a.numTiles - 1 - (wt >> 3) : (wt >> 3), sub = wt & 7;
         const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
         const int wx0 = tx * kTileW + (sub & 3) * 8,
                   wy0 = a.y0 + (ty * a.tileRowStride + a.tileRowOffset) * kTileH + (sub >> 2) * 4;

@@ -29,6 +29,14 @@ elif which == "rtsurf":  # the bench's step at N = 1: surface only
     for _ in range(3):
         ctx.rt_frame_device_async(0, H, surf.data_ptr())
     ctx.synchronize()
+elif which == "rt1":  # config 5's frame: 1 sample per pixel, surface only
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    ctx.set_frame(pkg.default_frame_params(0, W, H))
+    surf = torch.empty((H, W), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ctx.rt_frame_device_async(0, H, surf.data_ptr())
+    ctx.synchronize()
 elif which.startswith("rtpart"):  # one part of the frame split N ways (gather form, local surface): kernel time vs 1/N
     n = int(which[6:])
     ctx = pkg.Context(W, H)
