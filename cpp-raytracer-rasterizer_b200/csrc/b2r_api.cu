@@ -429,6 +429,8 @@ static int rt_launch_band(Ctx* c, int y0, int y1, float* d_col, b2r_intersection
     a.y0 = y0;
     a.y1 = y1;
     a.tilesX = (c->W + 31) / 32;
+    a.rcpTilesX = 1.0f / (float)a.tilesX;
+    a.rcpNN = 1.0f / (float)(c->hostFrame.aaN * c->hostFrame.aaN);
     a.tileRowStride = split ? split->stride : 1;
     a.tileRowOffset = split ? split->offset : 0;
     a.nPeerSurfaces = split ? split->nPeers : 0;

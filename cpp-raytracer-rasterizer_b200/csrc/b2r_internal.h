@@ -101,6 +101,8 @@ struct RtLaunch {
     unsigned* arriveCtr;  // local word, zero between launches: CTAs that have finished (used with arrive)
     unsigned* sched;   // 2 words, zero between launches: next warp tile to hand out, warps that have finished
     int batch;         // warp tiles per scheduler fetch (set by the launcher)
+    float rcpTilesX;   // 1.0f / tilesX (tile index -> tile row without an integer division)
+    float rcpNN;       // 1.0f / (aaN * aaN), used in place of the division by N*N when aaN is a power of two (same bits)
     int tileOrder;     // 0: tiles handed out top to bottom (needed when sub-bands are copied out in row order); 1: bottom to top
     int useFilter;
     int reuseLight;    // 1 (default): DirectLight only when the pixel's carried Intersection changed (see rt_trace.cu)

@@ -445,6 +445,10 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
     const float halfW = xdiv((float)a.W, 2.0f), halfH = xdiv((float)a.H, 2.0f);  // (float)SCREEN_WIDTH/2.0f :579
     const float stepAA = xdiv(1.0f, (float)(N - 1));                            // :593,596 (+inf when N == 1)
     const float invNN = (float)(N * N);
+    // :599 divides by N*N.  For N a power of two x * (1/(N*N)) is the same correctly rounded number as x / (N*N); N = 1
+    // needs nothing; otherwise a zero numerator (every pixel without a hit) skips div.rn's slow path: 0/n is 0 itself.
+    const bool nnPow2 = (N & (N - 1)) == 0;
+
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* myTileList = sTileList + warp * nChunks;  // non-empty chunks of this warp's tile
@@ -472,7 +476,15 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
     for (; base < numWarpTiles; base = nextBase, nextBase = nextBase < numWarpTiles ? fetch_batch() : numWarpTiles)
     for (int wt = base; wt < min(base + batch, numWarpTiles); ++wt) {
         const int tile = a.tileOrder ? a.numTiles - 1 - (wt >> 3) : (wt >> 3), sub = wt & 7;
-        const int ty = tile / a.tilesX, tx = tile - ty * a.tilesX;
+        // tile / tilesX without the integer-division sequence: tile < 2^22, so the float quotient is off by one at most
+        int ty = __float2int_rz(__int2float_rn(tile) * a.rcpTilesX), tx = tile - ty * a.tilesX;
+        if (tx < 0) {
+            --ty;
+            tx += a.tilesX;
+        } else if (tx >= a.tilesX) {
+            ++ty;
+            tx -= a.tilesX;
+        }
         const int wx0 = tx * kTileW + (sub & 3) * 8,
                   wy0 = a.y0 + (ty * a.tileRowStride + a.tileRowOffset) * kTileH + (sub >> 2) * 4;
         const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
@@ -750,7 +762,12 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
             y1 = xadd(y1, stepAA);  // :596
         }
         if (inside) {
-            avg = xdivs3(avg, invNN);  // :599
+            if (nnPow2) {  // :599
+                if (N > 1) avg = xscale3(avg, a.rcpNN);
+            } else {
+                avg = mk3(avg.x == 0.0f ? avg.x : xdiv(avg.x, invNN), avg.y == 0.0f ? avg.y : xdiv(avg.y, invNN),
+                          avg.z == 0.0f ? avg.z : xdiv(avg.z, invNN));
+            }
             const size_t idx = (size_t)y * (size_t)a.W + (size_t)x;  // P2: row stride = width
             if (a.colours) {
                 a.colours[3 * idx] = avg.x;
