@@ -37,6 +37,17 @@ elif which == "rt1":  # config 5's frame: 1 sample per pixel, surface only
     for _ in range(3):
         ctx.rt_frame_device_async(0, H, surf.data_ptr())
     ctx.synchronize()
+elif which == "rtsoft":  # config 3b: 1 sample per pixel, 16 jittered light samples
+    ctx = pkg.Context(W, H)
+    ctx.set_triangles(tris)
+    fp = pkg.default_frame_params(0, W, H)
+    fp.softShadowsEnabled = 1
+    fp.set_random_positions(pkg.jitter_table(1, [0, -0.5, -0.7]))
+    ctx.set_frame(fp)
+    surf = torch.empty((H, W), dtype=torch.int32, device=dev)
+    for _ in range(3):
+        ctx.rt_frame_device_async(0, H, surf.data_ptr())
+    ctx.synchronize()
 elif which.startswith("rtpart"):  # one part of the frame split N ways (gather form, local surface): kernel time vs 1/N
     n = int(which[6:])
     ctx = pkg.Context(W, H)
