@@ -192,16 +192,30 @@ int b2r_group_rt_frames(b2r_group* g, const b2r_frame_params* frames, int nframe
     const size_t slotBytes = bmp ? b2r_bmp_payload_bytes(g->W, g->H) : npx * 4;
     // Per device: up to kInFlight frames on the GPU, the other slots of its ring with the writer threads.  Writing a 25 MB
     // file takes several milliseconds (a frame is traced and copied in well under one), so what sets the pace is how
-    // many files are being written at once.
     // many files are being written at once (one GPU, 4K, /dev/shm: 3 slots 130-195 frames/s, 8 slots 520, 12 slots 550).
-    const int kRing = 8, kInFlight = 2, nSlots = g->n * kRing;
-    std::vector<void*> slots(nSlots, nullptr);
+    const int kInFlight = 2;
+    int kRing = 8, nSlots = 0;
+    std::vector<void*> slots;
     int rcAll = B2R_OK;
-    for (int s = 0; s < nSlots && !rcAll; ++s)
-        if (cudaHostAlloc(&slots[s], slotBytes, cudaHostAllocPortable) != cudaSuccess) {
-            cudaGetLastError();
-            rcAll = gfail(g, B2R_E_CUDA, "b2r_group_rt_frames: cudaHostAlloc of a frame slot failed");
+    for (;;) {  // page-locked memory is a limited resource: fall back to a shorter ring rather than fail
+        nSlots = g->n * kRing;
+        slots.assign(nSlots, nullptr);
+        bool ok = true;
+        for (int s = 0; s < nSlots && ok; ++s)
+            if (cudaHostAlloc(&slots[s], slotBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                ok = false;
+            }
+        if (ok) break;
+        for (void* p : slots)
+            if (p) cudaFreeHost(p);
+        if (kRing == 3) {
+            slots.assign(nSlots, nullptr);
+            rcAll = gfail(g, B2R_E_CUDA, "b2r_group_rt_frames: cudaHostAlloc of the frame slots failed");
+            break;
         }
+        kRing = kRing > 4 ? 4 : 3;
+    }
     Writers w;
     w.slotBusy.assign(nSlots, 0);
     const int W = g->W, H = g->H;
