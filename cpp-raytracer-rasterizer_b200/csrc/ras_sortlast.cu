@@ -551,6 +551,7 @@ __global__ void __launch_bounds__(256) ras_rows_kernel(const TriSetup* __restric
                 r.psx = xdiv_step(xsub(r.rp[0], r.lp[0]), fdx);  // :649, once per row instead of once per shaded pixel
                 r.psy = xdiv_step(xsub(r.rp[1], r.lp[1]), fdx);
             }
+            B2R_BOUND(rid, BAND ? (unsigned long long)ctr->nBig * (unsigned)bandH : (unsigned long long)nRows);
             rows[rid] = r;
         }
     }
@@ -592,6 +593,7 @@ __device__ __forceinline__ ShadeIn shade_fetch(const RasLaunch& a, unsigned long
     const unsigned tri = key_triangle(key);
     if (key & 1ull) {
         const int2 info = triInfo[tri];  // (index of the triangle's first row record, the y of that record)
+        B2R_BOUND(y - info.y, 1 << 22);  // kMaxRowsPerTriangle: the winner's triangle has a row at y
         const RowRec* r = rows + ((unsigned)info.x + (unsigned)(y - info.y));
         const float4 q0 = *reinterpret_cast<const float4*>(r);          // lx, rx, lz, rz
         const float2 q1 = *reinterpret_cast<const float2*>(r->lp);      // lp.x, lp.y

@@ -654,8 +654,10 @@ __global__ void __launch_bounds__(kTileThreads, 4) ras_tile_kernel(RasLaunch a, 
                 }
                 if (fits) {
                     const int r0 = (int)(S.rowBase[tid] - base), r1 = (int)(S.rowBase[tid + 1] - base);
-                    B2R_BOUND(r1 - 1, kRoundRows);
-                    for (int r = r0; r < r1; ++r) S.rowTri[r] = (unsigned short)tid;
+                    for (int r = r0; r < r1; ++r) {
+                        B2R_BOUND(r, kRoundRows);
+                        S.rowTri[r] = (unsigned short)tid;
+                    }
                 }
                 // ---- W: Interpolate (:615-637) of the small triangles' edges, one (triangle, edge) per thread ----
                 for (int t = tid; t < 3 * nt; t += kTileThreads) {

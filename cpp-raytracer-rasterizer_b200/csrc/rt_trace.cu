@@ -485,6 +485,8 @@ __global__ void __launch_bounds__(kThreads, SINGLE ? 4 : 3) rt_trace_shade_kerne
             ++ty;
             tx -= a.tilesX;
         }
+        B2R_BOUND(tx, a.tilesX);
+        B2R_BOUND(ty * a.tilesX + tx, a.numTiles);
         const int wx0 = tx * kTileW + (sub & 3) * 8,
                   wy0 = a.y0 + (ty * a.tileRowStride + a.tileRowOffset) * kTileH + (sub >> 2) * 4;
         const int x = wx0 + (lane & 7), y = wy0 + (lane >> 3);
