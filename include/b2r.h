@@ -287,6 +287,8 @@ int b2r_resolve_surface_multi_device_async(b2r_ctx* ctx, int y0, int y1, const f
  *                         each finished frame is either copied to surfaces + f*width*height (32-bit XRGB) or, when
  *                         bmp_pattern is given (a printf pattern with one %d), written as the 24-bit BMP
  *                         SDL_SaveBMP would write (raytracer.cpp:175) by writer threads while the GPUs go on.
+ *                         For the duration of the call every device holds a ring of up to 8 page-locked frame
+ *                         buffers (2 frames on the GPU, the others being written; fewer if page-locked memory is short).
  * A group is driven by one host thread.  Errors: negative B2R_E_* code, text from b2r_group_last_error. */
 typedef struct b2r_group b2r_group;
 int b2r_group_create(b2r_group** out, const int* devices, int n, int width, int height);
