@@ -915,7 +915,7 @@ cudaError_t launch_rt_trace_shade(Ctx* c, const RtLaunch& a0, cudaStream_t s) {
     if (resident) {
         a.xconst = a.fconst = nullptr;
         if (a.T <= 32) {
-            if (f.nLights == 1 && f.samples == 1 && f.nOrigins == 2 && (c->optRtVariant == 0 || c->optRtVariant == 5)) {
+            if (f.nLights == 1 && f.samples == 1 && f.nOrigins == 2 && (c->optRtVariant == 0 || c->optRtVariant == 4 || c->optRtVariant == 5)) {  // (4 and 5 do not change what this kernel is given)
                 for (int i = 0; i < 3; ++i) a.fr.light0[i] = f.origin[1][i], a.fr.power0[i] = f.lightPower[0][i];
                 return launch_variant<true, true, true, true>(c, a, smemRes, s);
             }
