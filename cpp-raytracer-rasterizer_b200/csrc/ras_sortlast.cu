@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kSmallThreads, 8) ras_small_kernel(RasLaunch a
     const int i = blockIdx.x * kSmallThreads + threadIdx.x;
     unsigned long long nTests = 0, nRows = 0, nDrawn = 0;
     // the three vertices: 9 floats at the head of the 64-byte record (60-byte scenes are repacked at upload), fetched
-    // together with the isCulled flag, which therefore does not gate the fetch
+    // next to the isCulled flag (the compiler may still sink them below the test of the flag; measured, that costs nothing)
     float t[12];
     unsigned char isCulled = 1;
     if (i < a.T) {
